@@ -1,0 +1,385 @@
+// oracle/ref_driver.cpp — TEST INFRASTRUCTURE ONLY (oracle). Not part of the product path.
+//
+// Runs the UNMODIFIED reference blocks (headers included by path from /root/reference/src,
+// never copied) through their own thread-per-block / stream<T> plumbing and exposes the
+// results through a plain C ABI so pytest (ctypes) and bench.py's cpu_baseline leg can call
+// them. Built only where /root/reference exists (this container) by oracle/Makefile into
+// oracle/_ref/; the built .so travels to the GPU box, the sources of the reference do not.
+//
+// Every entry point feeds `in` in the caller-given block partition (`blocks[nblocks]`,
+// each <= STREAM_BUFFER_SIZE) because several reference blocks have block-size-dependent
+// semantics (resampler schedule restart src/dsp/resampling.h:121, AGC src/dsp/processing.h:123).
+#include <dsp/block.h>
+#include <dsp/stream.h>
+#include <dsp/types.h>
+#include <dsp/window.h>
+#include <dsp/filter.h>
+#include <dsp/resampling.h>
+#include <dsp/processing.h>
+#include <dsp/demodulator.h>
+#include <dsp/pll.h>
+#include <dsp/vfo.h>
+#include <dsp/routing.h>
+
+#include <chrono>
+#include <thread>
+#include <vector>
+#include <cstring>
+
+using namespace dsp;
+
+namespace {
+
+template <class T>
+void feed(stream<T>* s, const T* data, const int* blocks, int nblocks) {
+    long long off = 0;
+    for (int b = 0; b < nblocks; b++) {
+        memcpy(s->writeBuf, data + off, (size_t)blocks[b] * sizeof(T));
+        if (!s->swap(blocks[b])) return;
+        off += blocks[b];
+    }
+}
+
+// Drain exactly `nblocks` swaps from `s` into `out`; returns total elements, per-swap counts in
+// out_counts (may be null).
+template <class T>
+long long drain(stream<T>* s, T* out, int nblocks, int* out_counts) {
+    long long total = 0;
+    for (int b = 0; b < nblocks; b++) {
+        int n = s->read();
+        if (n < 0) break;
+        if (out) memcpy(out + total, s->readBuf, (size_t)n * sizeof(T));
+        s->flush();
+        if (out_counts) out_counts[b] = n;
+        total += n;
+    }
+    return total;
+}
+
+struct Timer {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    double seconds() const {
+        return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+};
+
+template <class Tin, class Tout>
+long long pump(stream<Tin>* in, stream<Tout>* out, const Tin* data, const int* blocks, int nblocks,
+               Tout* result, int* out_counts, double* seconds, int out_swaps = -1) {
+    Timer t;
+    std::thread feeder([&] { feed(in, data, blocks, nblocks); });
+    long long total = drain(out, result, out_swaps < 0 ? nblocks : out_swaps, out_counts);
+    feeder.join();
+    if (seconds) *seconds = t.seconds();
+    return total;
+}
+
+template <int ORDER>
+long long costas_impl(float bw, const float* in, const int* blocks, int nblocks, float* out, double* seconds) {
+    stream<complex_t> src;
+    CostasLoop<ORDER> c(&src, bw);
+    c.start();
+    long long n = pump(&src, &c.out, (const complex_t*)in, blocks, nblocks, (complex_t*)out, nullptr, seconds);
+    c.stop();
+    return n;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ref_stream_buffer_size() { return STREAM_BUFFER_SIZE; }
+
+// ---- tap design: src/dsp/window.h ----------------------------------------------------------
+int ref_blackman_tap_count(float cutoff, float transWidth, float sampleRate) {
+    filter_window::BlackmanWindow w(cutoff, transWidth, sampleRate);
+    return w.getTapCount();
+}
+void ref_blackman_taps(float cutoff, float transWidth, float sampleRate, float* taps, int tapCount, float factor) {
+    filter_window::BlackmanWindow w(cutoff, transWidth, sampleRate);
+    w.createTaps(taps, tapCount, factor);
+}
+int ref_blackman_bandpass_tap_count(float cutoff, float transWidth, float offset, float sampleRate) {
+    filter_window::BlackmanBandpassWindow w(cutoff, transWidth, offset, sampleRate);
+    return w.getTapCount();
+}
+void ref_blackman_bandpass_taps(float cutoff, float transWidth, float offset, float sampleRate, float* taps,
+                                int tapCount, float factor) {
+    filter_window::BlackmanBandpassWindow w(cutoff, transWidth, offset, sampleRate);
+    w.createTaps(taps, tapCount, factor);
+}
+void ref_rrc_taps(int tapCount, float sampleRate, float baudRate, float alpha, float* taps) {
+    RRCTaps w(tapCount, sampleRate, baudRate, alpha);
+    w.createTaps(taps, tapCount);
+}
+
+// ---- FIR: src/dsp/filter.h:9-90 --------------------------------------------------------------
+// NOTE the reference leaves the first-block history uninitialised (filter.h:28); glibc returns
+// fresh zero pages for an allocation this large, and callers exclude the first tapCount-1
+// outputs from parity anyway.
+long long ref_fir_cf32(float cutoff, float transWidth, float sampleRate, const float* in, const int* blocks,
+                       int nblocks, float* out, double* seconds) {
+    filter_window::BlackmanWindow win(cutoff, transWidth, sampleRate);
+    stream<complex_t> src;
+    FIR<complex_t> fir(&src, &win);
+    fir.start();
+    long long n = pump(&src, &fir.out, (const complex_t*)in, blocks, nblocks, (complex_t*)out, nullptr, seconds);
+    fir.stop();
+    return n;
+}
+long long ref_fir_f32(float cutoff, float transWidth, float sampleRate, const float* in, const int* blocks,
+                      int nblocks, float* out, double* seconds) {
+    filter_window::BlackmanWindow win(cutoff, transWidth, sampleRate);
+    stream<float> src;
+    FIR<float> fir(&src, &win);
+    fir.start();
+    long long n = pump(&src, &fir.out, in, blocks, nblocks, out, nullptr, seconds);
+    fir.stop();
+    return n;
+}
+
+// ---- PolyphaseResampler: src/dsp/resampling.h:9-190 -----------------------------------------
+// Window is BlackmanWindow(cutoff, transWidth, winSampleRate). `vfo_style` != 0 repeats what
+// VFO::init does (src/dsp/vfo.h:29-33): re-rate the window to inSR*interp and updateWindow.
+long long ref_resamp_cf32(float cutoff, float transWidth, float winSampleRate, float inSR, float outSR,
+                          int vfo_style, const float* in, const int* blocks, int nblocks, float* out,
+                          int* out_counts, int* interp, int* decim, double* seconds) {
+    filter_window::BlackmanWindow win(cutoff, transWidth, winSampleRate);
+    stream<complex_t> src;
+    PolyphaseResampler<complex_t> rs(&src, &win, inSR, outSR);
+    if (vfo_style) {
+        win.setSampleRate(inSR * rs.getInterpolation());
+        rs.updateWindow(&win);
+    }
+    if (interp) *interp = rs.getInterpolation();
+    if (decim) *decim = rs.getDecimation();
+    rs.start();
+    long long n = pump(&src, &rs.out, (const complex_t*)in, blocks, nblocks, (complex_t*)out, out_counts, seconds);
+    rs.stop();
+    return n;
+}
+long long ref_resamp_f32(float cutoff, float transWidth, float winSampleRate, float inSR, float outSR,
+                         const float* in, const int* blocks, int nblocks, float* out, int* out_counts,
+                         int* interp, int* decim, double* seconds) {
+    filter_window::BlackmanWindow win(cutoff, transWidth, winSampleRate);
+    stream<float> src;
+    PolyphaseResampler<float> rs(&src, &win, inSR, outSR);
+    if (interp) *interp = rs.getInterpolation();
+    if (decim) *decim = rs.getDecimation();
+    rs.start();
+    long long n = pump(&src, &rs.out, in, blocks, nblocks, out, out_counts, seconds);
+    rs.stop();
+    return n;
+}
+
+// ---- PowerDecimator: src/dsp/resampling.h:192-258 --------------------------------------------
+long long ref_power_decim(unsigned int power, const float* in, const int* blocks, int nblocks, float* out,
+                          int* out_counts) {
+    stream<complex_t> src;
+    PowerDecimator pd(&src, power);
+    pd.start();
+    long long n = pump(&src, &pd.out, (const complex_t*)in, blocks, nblocks, (complex_t*)out, out_counts, nullptr);
+    pd.stop();
+    return n;
+}
+
+// ---- FrequencyXlator: src/dsp/processing.h:9-82 ---------------------------------------------
+long long ref_xlator(float sampleRate, float freq, const float* in, const int* blocks, int nblocks, float* out,
+                     double* seconds) {
+    stream<complex_t> src;
+    FrequencyXlator<complex_t> x(&src, sampleRate, freq);
+    x.start();
+    long long n = pump(&src, &x.out, (const complex_t*)in, blocks, nblocks, (complex_t*)out, nullptr, seconds);
+    x.stop();
+    return n;
+}
+// phase increment exactly as the reference derives it (processing.h:21), for the GPU side to reuse
+void ref_xlator_phase_delta(float sampleRate, float freq, float* re, float* im) {
+    lv_32fc_t d = lv_cmake(std::cos((freq / sampleRate) * 2.0f * FL_M_PI), std::sin((freq / sampleRate) * 2.0f * FL_M_PI));
+    *re = d.real();
+    *im = d.imag();
+}
+// raw rotator call (shim semantics) with explicit phase in/out, one call per block
+void ref_rotator(const float* in, float* out, float inc_re, float inc_im, float* phase_re, float* phase_im,
+                 const int* blocks, int nblocks) {
+    lv_32fc_t ph = lv_cmake(*phase_re, *phase_im);
+    long long off = 0;
+    for (int b = 0; b < nblocks; b++) {
+        volk_32fc_s32fc_x2_rotator_32fc((lv_32fc_t*)out + off, (const lv_32fc_t*)in + off, lv_cmake(inc_re, inc_im), &ph,
+                                        blocks[b]);
+        off += blocks[b];
+    }
+    *phase_re = ph.real();
+    *phase_im = ph.imag();
+}
+
+// ---- VFO: src/dsp/vfo.h ----------------------------------------------------------------------
+long long ref_vfo(float offset, float inSR, float outSR, float bandWidth, const float* in, const int* blocks,
+                  int nblocks, float* out, int* out_counts, double* seconds) {
+    stream<complex_t> src;
+    VFO vfo(&src, offset, inSR, outSR, bandWidth);
+    vfo.start();
+    long long n = pump(&src, vfo.out, (const complex_t*)in, blocks, nblocks, (complex_t*)out, out_counts, seconds);
+    return n;  // VFO::stop() is a no-op in the reference (vfo.h:44-48); member dtors stop the workers
+}
+// taps/I/D a VFO ends up with (vfo.h:26-33), re-derived through the same public calls
+int ref_vfo_design(float inSR, float outSR, float bandWidth, float* taps, int maxTaps, int* interp, int* decim) {
+    float realCutoff = std::min<float>(bandWidth, std::min<float>(inSR, outSR)) / 2.0f;
+    filter_window::BlackmanWindow win;
+    win.init(realCutoff, realCutoff, inSR);
+    stream<complex_t> dummy;
+    PolyphaseResampler<complex_t> rs(&dummy, &win, inSR, outSR);
+    win.setSampleRate(inSR * rs.getInterpolation());
+    int tc = win.getTapCount();
+    if (interp) *interp = rs.getInterpolation();
+    if (decim) *decim = rs.getDecimation();
+    if (taps && tc <= maxTaps) win.createTaps(taps, tc, rs.getInterpolation());
+    return tc;
+}
+
+// ---- FM demod: src/dsp/demodulator.h:14-30,32-182 --------------------------------------------
+long long ref_fm_demod(float sampleRate, float deviation, const float* in, const int* blocks, int nblocks,
+                       float* out, double* seconds) {
+    stream<complex_t> src;
+    FloatFMDemod d(&src, sampleRate, deviation);
+    d.start();
+    long long n = pump(&src, &d.out, (const complex_t*)in, blocks, nblocks, out, nullptr, seconds);
+    d.stop();
+    return n;
+}
+long long ref_fm_demod_stereo(float sampleRate, float deviation, const float* in, const int* blocks, int nblocks,
+                              float* out) {
+    stream<complex_t> src;
+    FMDemod d(&src, sampleRate, deviation);
+    d.start();
+    long long n = pump(&src, &d.out, (const complex_t*)in, blocks, nblocks, (stereo_t*)out, nullptr, nullptr);
+    d.stop();
+    return n;
+}
+float ref_fast_arctan2(float y, float x) { return fast_arctan2(y, x); }
+
+// ---- the fused chain as the reference composes it: VFO -> FloatFMDemod (3 worker threads) ----
+long long ref_vfo_fm(float offset, float inSR, float outSR, float bandWidth, float deviation, const float* in,
+                     const int* blocks, int nblocks, float* audio, int* out_counts, double* seconds) {
+    stream<complex_t> src;
+    VFO vfo(&src, offset, inSR, outSR, bandWidth);
+    FloatFMDemod dem(vfo.out, outSR, deviation);
+    vfo.start();
+    dem.start();
+    long long n = pump(&src, &dem.out, (const complex_t*)in, blocks, nblocks, audio, out_counts, seconds);
+    dem.stop();
+    return n;
+}
+
+// ---- channelizer: one Splitter fanning the same wideband stream to nch VFO+FloatFMDemod -------
+// (src/dsp/routing.h:47-57). audio is [nch][outPerChannel] row-major; returns outputs/channel.
+long long ref_channelizer_fm(int nch, const float* offsets, float inSR, float outSR, float bandWidth,
+                             float deviation, const float* in, const int* blocks, int nblocks, float* audio,
+                             long long audio_stride, double* seconds) {
+    stream<complex_t> src;
+    Splitter<complex_t> split(&src);
+    std::vector<stream<complex_t>*> legs(nch);
+    std::vector<VFO*> vfos(nch);
+    std::vector<FloatFMDemod*> dems(nch);
+    for (int c = 0; c < nch; c++) {
+        legs[c] = new stream<complex_t>();
+        split.bindStream(legs[c]);
+        vfos[c] = new VFO(legs[c], offsets[c], inSR, outSR, bandWidth);
+        dems[c] = new FloatFMDemod(vfos[c]->out, outSR, deviation);
+    }
+    for (int c = 0; c < nch; c++) { vfos[c]->start(); dems[c]->start(); }
+    split.start();
+    Timer t;
+    std::thread feeder([&] { feed(&src, (const complex_t*)in, blocks, nblocks); });
+    std::vector<std::thread> drains;
+    std::vector<long long> totals(nch, 0);
+    for (int c = 0; c < nch; c++)
+        drains.emplace_back([&, c] { totals[c] = drain(&dems[c]->out, audio + (long long)c * audio_stride, nblocks, nullptr); });
+    feeder.join();
+    for (auto& d : drains) d.join();
+    if (seconds) *seconds = t.seconds();
+    split.stop();
+    for (int c = 0; c < nch; c++) { dems[c]->stop(); }
+    long long per = totals.empty() ? 0 : totals[0];
+    for (int c = 0; c < nch; c++) { delete dems[c]; delete vfos[c]; delete legs[c]; }
+    return per;
+}
+
+// ---- recurrent blocks ---------------------------------------------------------------------------
+// BFMDeemp: src/dsp/filter.h:92-172
+long long ref_deemp(float sampleRate, float tau, const float* in, const int* blocks, int nblocks, float* out,
+                    double* seconds) {
+    stream<stereo_t> src;
+    BFMDeemp d(&src, sampleRate, tau);
+    d.start();
+    long long n = pump(&src, &d.out, (const stereo_t*)in, blocks, nblocks, (stereo_t*)out, nullptr, seconds);
+    d.stop();
+    return n;
+}
+// AGC: src/dsp/processing.h:84-147
+long long ref_agc(float fallRate, float sampleRate, const float* in, const int* blocks, int nblocks, float* out,
+                  double* seconds) {
+    stream<float> src;
+    AGC a(&src, fallRate, sampleRate);
+    a.start();
+    long long n = pump(&src, &a.out, in, blocks, nblocks, out, nullptr, seconds);
+    a.stop();
+    return n;
+}
+// ComplexAGC: src/dsp/processing.h:236-297
+long long ref_complex_agc(float setPoint, float maxGain, float rate, const float* in, const int* blocks,
+                          int nblocks, float* out, double* seconds) {
+    stream<complex_t> src;
+    ComplexAGC a(&src, setPoint, maxGain, rate);
+    a.start();
+    long long n = pump(&src, &a.out, (const complex_t*)in, blocks, nblocks, (complex_t*)out, nullptr, seconds);
+    a.stop();
+    return n;
+}
+// FeedForwardAGC: src/dsp/processing.h:149-234. A run() that has not yet collected 1024 samples
+// returns without swapping (:188-191), so the number of swaps can be < nblocks; out_counts[b] is
+// the swap size (== input block size, :221) and valid_counts[b] the number of meaningful outputs.
+long long ref_ff_agc_cf32(const float* in, const int* blocks, int nblocks, float* out, int* valid_counts,
+                          int* nswaps) {
+    stream<complex_t> src;
+    FeedForwardAGC<complex_t> a(&src);
+    // replicate the block's own bookkeeping to know how many swaps to expect
+    int inBuffer = 0, swaps = 0;
+    std::vector<int> valid;
+    for (int b = 0; b < nblocks; b++) {
+        inBuffer += blocks[b];
+        if (inBuffer < 1024) continue;
+        int toProcess = inBuffer - 1024 + 1;
+        inBuffer -= toProcess;
+        valid.push_back(toProcess);
+        swaps++;
+    }
+    a.start();
+    std::thread feeder([&] { feed(&src, (const complex_t*)in, blocks, nblocks); });
+    long long total = 0;
+    for (int s = 0; s < swaps; s++) {
+        int n = a.out.read();
+        if (n < 0) break;
+        memcpy((complex_t*)out + total, a.out.readBuf, (size_t)valid[s] * sizeof(complex_t));
+        a.out.flush();
+        if (valid_counts) valid_counts[s] = valid[s];
+        total += valid[s];
+    }
+    feeder.join();
+    // the last run() may still be blocked in read(); stop() unblocks it
+    a.stop();
+    if (nswaps) *nswaps = swaps;
+    return total;
+}
+// CostasLoop<ORDER>: src/dsp/pll.h
+long long ref_costas(int order, float loopBandwidth, const float* in, const int* blocks, int nblocks, float* out,
+                     double* seconds) {
+    switch (order) {
+        case 2: return costas_impl<2>(loopBandwidth, in, blocks, nblocks, out, seconds);
+        case 4: return costas_impl<4>(loopBandwidth, in, blocks, nblocks, out, seconds);
+        case 8: return costas_impl<8>(loopBandwidth, in, blocks, nblocks, out, seconds);
+    }
+    return -1;
+}
+
+}  // extern "C"
