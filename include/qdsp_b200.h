@@ -1,0 +1,220 @@
+/* include/qdsp_b200.h — C ABI of libqdsp_b200.so (B200 / sm_100a).
+ *
+ * This is the drop-in boundary underneath the reference's header-only `dsp::` block API
+ * (AlexandreRouma/qdsp, src/dsp/*.h). The reference has no FFI seam of its own: every block is a
+ * C++ class whose `run()` does the arithmetic on the CPU (mostly through VOLK). Each entry point
+ * below replaces the body of one `run()` (cited per function) and is what the new
+ * `include/dsp/*.h` mirror headers, the ctypes binding (`qdsp_b200/lib.py`) and `bench.py` call.
+ *
+ * Conventions
+ *   - plain C types only; all `*_dev` pointers are CUDA device pointers owned by the caller;
+ *     `qdsp_stream_t` is a `cudaStream_t` passed as `void*` (NULL = the legacy default stream);
+ *   - every `*_process` call is asynchronous on that stream and allocation-free on the hot path;
+ *   - return value mirrors `run()`: number of elements produced (>= 0) or -1 on error, with the
+ *     text available from `qdsp_last_error()`;
+ *   - per-block state (history tail, NCO phase, demod phase, IIR/AGC/PLL scalars) lives on the
+ *     device inside the opaque handle and can be read/written with `*_get_state/_set_state`
+ *     (used for checkpointing, parity injection and multi-GPU time-sharding);
+ *   - where the reference's result depends on how the stream was cut into `run()` calls
+ *     (resampler schedule restart, AGC decay) the batch entry points take the block partition:
+ *     `blocks[nblocks]` (sizes, sum == count) or, with `blocks == NULL`, a uniform `nblocks`-way
+ *     partition described by `block_size` (last block short).
+ *   - there is NO CPU fallback: if no CUDA device is usable every compute entry point fails.
+ */
+#ifndef QDSP_B200_H
+#define QDSP_B200_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QDSP_ABI_VERSION 1
+typedef void* qdsp_stream_t;
+enum { QDSP_F32 = 0, QDSP_CF32 = 1 }; /* element type of a stream: float or {float re,im} (== stereo_t) */
+
+/* ---- runtime plumbing (replaces volk_malloc/volk_free in src/dsp/stream.h:25-31) ------------- */
+int qdsp_abi_version(void);
+const char* qdsp_last_error(void);
+int qdsp_device_count(void);
+int qdsp_set_device(int device);
+int qdsp_get_device(void);
+void* qdsp_malloc_device(size_t bytes);
+void qdsp_free_device(void* p);
+void* qdsp_malloc_pinned(size_t bytes);
+void qdsp_free_pinned(void* p);
+int qdsp_memset_device(void* dst_dev, int value, size_t bytes, qdsp_stream_t s);
+int qdsp_copy_h2d(void* dst_dev, const void* src_host, size_t bytes, qdsp_stream_t s);
+int qdsp_copy_d2h(void* dst_host, const void* src_dev, size_t bytes, qdsp_stream_t s);
+int qdsp_copy_d2d(void* dst_dev, const void* src_dev, size_t bytes, qdsp_stream_t s);
+int qdsp_copy_peer(void* dst_dev, int dst_device, const void* src_dev, int src_device, size_t bytes, qdsp_stream_t s);
+int qdsp_enable_peer_access(int device, int peer);
+qdsp_stream_t qdsp_stream_create(void);
+void qdsp_stream_destroy(qdsp_stream_t s);
+int qdsp_stream_sync(qdsp_stream_t s);
+/* number of kernels this library has launched in this process (bench.py "gpu_launches") */
+long long qdsp_launch_count(void);
+
+/* ---- tap design, host side, bit-exact with the reference (src/dsp/window.h) ------------------ */
+int qdsp_blackman_tap_count(float cutoff, float transWidth, float sampleRate);                 /* window.h:36-50 */
+void qdsp_blackman_taps(float cutoff, float transWidth, float sampleRate, float* taps, int tapCount,
+                        float factor);                                                        /* window.h:52-70 */
+void qdsp_blackman_bandpass_taps(float cutoff, float transWidth, float offset, float sampleRate, float* taps,
+                                 int tapCount, float factor);                                 /* window.h:120-141 */
+void qdsp_rrc_taps(int tapCount, float sampleRate, float baudRate, float alpha, float* taps);  /* window.h:184-229 */
+void qdsp_rates_to_ratio(float inSampleRate, float outSampleRate, int* interp, int* decim);    /* resampling.h:28-30 */
+/* VFO::init tap design (vfo.h:26-33): returns tap count; fills taps (if maxTaps suffices), I and D */
+int qdsp_vfo_design(float inSampleRate, float outSampleRate, float bandWidth, float* taps, int maxTaps, int* interp,
+                    int* decim);
+/* resampler schedule of one block (resampling.h:121-125): phase[k] = (k*D)%I, index[k] = (k*D)/I */
+int qdsp_resamp_schedule(int interp, int decim, int count, int* phase, int* index);
+
+/* ---- FIR<float> / FIR<complex_t>::run, src/dsp/filter.h:51-74 ------------------------------- */
+typedef struct qdsp_fir qdsp_fir;
+qdsp_fir* qdsp_fir_create(int dtype, const float* taps, int tapCount);
+void qdsp_fir_destroy(qdsp_fir* h);
+int qdsp_fir_set_taps(qdsp_fir* h, const float* taps, int tapCount);      /* FIR::updateWindow, filter.h:43-49 */
+long long qdsp_fir_process(qdsp_fir* h, const void* in_dev, void* out_dev, long long count, qdsp_stream_t s);
+int qdsp_fir_history_len(qdsp_fir* h);                                     /* tapCount - 1 elements */
+int qdsp_fir_get_history(qdsp_fir* h, void* hist_host);
+int qdsp_fir_set_history(qdsp_fir* h, const void* hist_host);
+/* time-sharding halo: adopt the previous shard's last (tapCount-1) elements, read from a device
+ * pointer that may live on a peer GPU (NVLink P2P); replaces the memmove at filter.h:71 */
+int qdsp_fir_import_tail(qdsp_fir* h, const void* tail_dev, int src_device, qdsp_stream_t s);
+int qdsp_fir_reset(qdsp_fir* h);
+/* force a kernel variant: 0 = auto, 1 = generic, 2 = register-blocked sm_100a kernel */
+int qdsp_fir_set_variant(qdsp_fir* h, int variant);
+
+/* ---- PolyphaseResampler<T>::run, src/dsp/resampling.h:99-132 (+buildTapPhases :137-166) ----- */
+typedef struct qdsp_resamp qdsp_resamp;
+qdsp_resamp* qdsp_resamp_create(int dtype, const float* taps, int tapCount, int interp, int decim);
+void qdsp_resamp_destroy(qdsp_resamp* h);
+int qdsp_resamp_set_taps(qdsp_resamp* h, const float* taps, int tapCount);
+int qdsp_resamp_taps_per_phase(qdsp_resamp* h);
+long long qdsp_resamp_out_count(qdsp_resamp* h, long long count);          /* calcOutSize, resampling.h:95-97 */
+/* batch of run() calls over one contiguous input; out_counts (host, optional) gets per-block counts */
+long long qdsp_resamp_process(qdsp_resamp* h, const void* in_dev, void* out_dev, long long count, const int* blocks,
+                              int nblocks, int block_size, int* out_counts, qdsp_stream_t s);
+/* device-evaluated schedule of the same batch (parity of indices): phase/index per output */
+long long qdsp_resamp_schedule_device(qdsp_resamp* h, long long count, const int* blocks, int nblocks, int block_size,
+                                      int* phase_dev, long long* index_dev, qdsp_stream_t s);
+int qdsp_resamp_history_len(qdsp_resamp* h);                               /* tapsPerPhase elements */
+int qdsp_resamp_get_history(qdsp_resamp* h, void* hist_host);
+int qdsp_resamp_set_history(qdsp_resamp* h, const void* hist_host);
+int qdsp_resamp_reset(qdsp_resamp* h);
+int qdsp_resamp_set_variant(qdsp_resamp* h, int variant);
+
+/* ---- PowerDecimator::run, src/dsp/resampling.h:220-249 ---------------------------------------- */
+long long qdsp_power_decim_process(unsigned int power, const void* in_dev, void* out_dev, long long count,
+                                   qdsp_stream_t s);
+
+/* ---- FrequencyXlator<complex_t>::run + VOLK rotator, src/dsp/processing.h:55-70 ------------- */
+typedef struct qdsp_xlator qdsp_xlator;
+qdsp_xlator* qdsp_xlator_create(float sampleRate, float freq);             /* init, processing.h:16-24 */
+void qdsp_xlator_destroy(qdsp_xlator* h);
+int qdsp_xlator_set_frequency(qdsp_xlator* h, float sampleRate, float freq); /* processing.h:36-49 */
+void qdsp_xlator_get_phase_delta(qdsp_xlator* h, float* re, float* im);
+void qdsp_xlator_get_phase(qdsp_xlator* h, float* re, float* im);          /* VOLK `lv_32fc_t* phase` */
+void qdsp_xlator_set_phase(qdsp_xlator* h, float re, float im);
+long long qdsp_xlator_process(qdsp_xlator* h, const void* in_dev, void* out_dev, long long count, qdsp_stream_t s);
+
+/* ---- FloatFMDemod / FMDemod::run, src/dsp/demodulator.h:81-99 / 158-178 ---------------------- */
+typedef struct qdsp_fmdemod qdsp_fmdemod;
+qdsp_fmdemod* qdsp_fmdemod_create(float sampleRate, float deviation, int stereo_out);
+void qdsp_fmdemod_destroy(qdsp_fmdemod* h);
+float qdsp_fmdemod_get_phase(qdsp_fmdemod* h);
+int qdsp_fmdemod_set_phase(qdsp_fmdemod* h, float phase);
+long long qdsp_fmdemod_process(qdsp_fmdemod* h, const void* in_dev, void* out_dev, long long count, qdsp_stream_t s);
+
+/* ---- fused VFO (vfo.h:19-36: Xlator(-offset) -> PolyphaseResampler) -> FloatFMDemod ---------- *
+ * One pass: the translated and the resampled IQ never reach HBM unless iq_out_dev != NULL.        */
+typedef struct qdsp_vfofm qdsp_vfofm;
+qdsp_vfofm* qdsp_vfofm_create(float offset, float inSampleRate, float outSampleRate, float bandWidth,
+                              float deviation);
+void qdsp_vfofm_destroy(qdsp_vfofm* h);
+int qdsp_vfofm_design(qdsp_vfofm* h, int* tapCount, int* interp, int* decim);
+int qdsp_vfofm_set_offset(qdsp_vfofm* h, float offset);                    /* VFO::setOffset, vfo.h:87-90 */
+long long qdsp_vfofm_out_count(qdsp_vfofm* h, long long count, const int* blocks, int nblocks, int block_size);
+long long qdsp_vfofm_process(qdsp_vfofm* h, const void* in_dev, float* audio_out_dev, void* iq_out_dev,
+                             long long count, const int* blocks, int nblocks, int block_size, int* out_counts,
+                             qdsp_stream_t s);
+/* same call with HOST buffers: chunked, double-buffered H2D / D2H inside (the end-to-end path) */
+long long qdsp_vfofm_process_host(qdsp_vfofm* h, const void* in_host, float* audio_out_host, long long count,
+                                  int block_size, qdsp_stream_t s);
+int qdsp_vfofm_reset(qdsp_vfofm* h);
+int qdsp_vfofm_set_variant(qdsp_vfofm* h, int variant);
+/* time-sharding: start this shard at absolute stream sample `start` (NCO phase in closed form),
+ * history/demod state imported from the previous shard */
+int qdsp_vfofm_seek(qdsp_vfofm* h, long long start);
+int qdsp_vfofm_import_tail(qdsp_vfofm* h, const void* tail_dev, int src_device, qdsp_stream_t s);
+int qdsp_vfofm_history_len(qdsp_vfofm* h);
+
+/* ---- channelizer: nch x [VFO -> FloatFMDemod] off one Splitter (routing.h:47-57) ------------ */
+typedef struct qdsp_channelizer qdsp_channelizer;
+qdsp_channelizer* qdsp_channelizer_create(int nch, const float* offsets, float inSampleRate, float outSampleRate,
+                                          float bandWidth, float deviation);
+void qdsp_channelizer_destroy(qdsp_channelizer* h);
+int qdsp_channelizer_design(qdsp_channelizer* h, int* tapCount, int* interp, int* decim);
+/* audio_out_dev is [nch][out_stride] floats; returns outputs per channel */
+long long qdsp_channelizer_process(qdsp_channelizer* h, const void* in_dev, float* audio_out_dev,
+                                   long long out_stride, long long count, const int* blocks, int nblocks,
+                                   int block_size, qdsp_stream_t s);
+int qdsp_channelizer_reset(qdsp_channelizer* h);
+int qdsp_channelizer_set_variant(qdsp_channelizer* h, int variant);
+
+/* ---- recurrent blocks (chunked block-parallel scans) ----------------------------------------- */
+/* BFMDeemp::run, src/dsp/filter.h:129-158 (stereo_t in/out, state lastOutL/R) */
+typedef struct qdsp_deemp qdsp_deemp;
+qdsp_deemp* qdsp_deemp_create(float sampleRate, float tau);
+void qdsp_deemp_destroy(qdsp_deemp* h);
+long long qdsp_deemp_process(qdsp_deemp* h, const void* in_dev, void* out_dev, long long count, qdsp_stream_t s);
+int qdsp_deemp_get_state(qdsp_deemp* h, float* lastL, float* lastR);
+int qdsp_deemp_set_state(qdsp_deemp* h, float lastL, float lastR);
+
+/* AGC::run, src/dsp/processing.h:119-134 (per-block decay, block max, scale) */
+typedef struct qdsp_agc qdsp_agc;
+qdsp_agc* qdsp_agc_create(float fallRate, float sampleRate);
+void qdsp_agc_destroy(qdsp_agc* h);
+long long qdsp_agc_process(qdsp_agc* h, const float* in_dev, float* out_dev, long long count, const int* blocks,
+                           int nblocks, int block_size, qdsp_stream_t s);
+int qdsp_agc_get_state(qdsp_agc* h, float* level);
+int qdsp_agc_set_state(qdsp_agc* h, float level);
+
+/* ComplexAGC::run, src/dsp/processing.h:271-286 */
+typedef struct qdsp_cagc qdsp_cagc;
+qdsp_cagc* qdsp_cagc_create(float setPoint, float maxGain, float rate);
+void qdsp_cagc_destroy(qdsp_cagc* h);
+long long qdsp_cagc_process(qdsp_cagc* h, const void* in_dev, void* out_dev, long long count, qdsp_stream_t s);
+int qdsp_cagc_get_state(qdsp_cagc* h, float* gain);
+int qdsp_cagc_set_state(qdsp_cagc* h, float gain);
+
+/* FeedForwardAGC<complex_t>::run, src/dsp/processing.h:175-223; returns valid outputs (toProcess) */
+typedef struct qdsp_ffagc qdsp_ffagc;
+qdsp_ffagc* qdsp_ffagc_create(int dtype);
+void qdsp_ffagc_destroy(qdsp_ffagc* h);
+long long qdsp_ffagc_process(qdsp_ffagc* h, const void* in_dev, void* out_dev, long long count, qdsp_stream_t s);
+
+/* CostasLoop<ORDER>::run, src/dsp/pll.h:47-102; state = {vcoFrequency, vcoPhase, lastVCO.re, lastVCO.im} */
+typedef struct qdsp_costas qdsp_costas;
+qdsp_costas* qdsp_costas_create(int order, float loopBandwidth);
+void qdsp_costas_destroy(qdsp_costas* h);
+long long qdsp_costas_process(qdsp_costas* h, const void* in_dev, void* out_dev, long long count, qdsp_stream_t s);
+int qdsp_costas_get_state(qdsp_costas* h, float state[4]);
+int qdsp_costas_set_state(qdsp_costas* h, const float state[4]);
+/* chunk length / warm-up of the block-parallel scan (0,0 = strictly sequential single thread);
+ * after a process call, max boundary phase residual (validity check of the stitched scan) */
+int qdsp_costas_set_chunking(qdsp_costas* h, int chunk, int warmup);
+float qdsp_costas_last_residual(qdsp_costas* h);
+
+/* ---- device-side synthetic IQ (bench inputs; same integer recipe as qdsp_b200/synth.py) ------ */
+int qdsp_synth_uniform_cf32(void* out_dev, unsigned long long seed, long long start, long long count, qdsp_stream_t s);
+int qdsp_synth_fm_cf32(void* out_dev, long long start, long long count, long long fs, long long fc, long long fm,
+                       double dev, double amp, double noise_amp, unsigned long long noise_seed, qdsp_stream_t s);
+
+/* ---- microbenchmarks used by bench.py to measure the FP32 roofline denominator -------------- */
+/* runs `iters` dependent-chain FMA iterations on every SM; returns achieved TFLOP/s (2 flop/FMA) */
+double qdsp_measure_fp32_peak(int packed /*0: FFMA, 1: FFMA2*/, int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QDSP_B200_H */

@@ -1,0 +1,675 @@
+"""Host-side mirror of the reference's ``dsp::`` block interface over the C ABI.
+
+Class names, constructor/`init` argument order and setter names follow the reference headers
+(``src/dsp/{window,filter,resampling,processing,demodulator,pll,vfo}.h``); the thread-per-block
+`start()/stop()` machinery is not reproduced here — a block's `run()` body is `process(...)`, which
+enqueues sm_100a kernels on a CUDA stream. (The C++ mirror with `stream<T>`/`generic_block` lives in
+``include/dsp``.)  Two calling styles:
+
+* ``process(x, block=...)``            numpy in -> numpy out (H2D, kernels, D2H; convenience / tests)
+* ``process_device(in_ptr, out_ptr, n, ...)``  raw device pointers, asynchronous (bench / pipelines)
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import lib as _lib
+from .lib import CF32, F32, QdspError, check
+
+
+def _L():
+    return _lib.load()
+
+
+def _fptr(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _iptr(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+class DevBuf:
+    """A device allocation owned by Python (cudaMalloc through the C ABI)."""
+
+    def __init__(self, nbytes: int):
+        _lib.require_device()
+        self.nbytes = int(nbytes)
+        self.ptr = check(_L().qdsp_malloc_device(max(self.nbytes, 16)), "qdsp_malloc_device")
+
+    @classmethod
+    def from_numpy(cls, a: np.ndarray, stream=None) -> "DevBuf":
+        a = np.ascontiguousarray(a)
+        b = cls(a.nbytes)
+        if a.nbytes:
+            check(_L().qdsp_copy_h2d(b.ptr, a.ctypes.data, a.nbytes, stream), "h2d")
+            check(_L().qdsp_stream_sync(stream), "sync")
+        return b
+
+    def to_numpy(self, dtype, count: int, stream=None, offset_bytes: int = 0) -> np.ndarray:
+        out = np.empty(count, dtype)
+        if out.nbytes:
+            check(_L().qdsp_stream_sync(stream), "sync")
+            check(_L().qdsp_copy_d2h(out.ctypes.data, self.ptr + offset_bytes, out.nbytes, stream), "d2h")
+            check(_L().qdsp_stream_sync(stream), "sync")
+        return out
+
+    def free(self):
+        if getattr(self, "ptr", None):
+            _L().qdsp_free_device(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _blocks_arg(n: int, block):
+    """block: None/int -> uniform partition (block_size); list/array -> explicit sizes."""
+    if block is None:
+        return None, 0, 0
+    if np.isscalar(block):
+        return None, 0, int(block)
+    b = np.ascontiguousarray(block, dtype=np.int32)
+    if int(b.sum()) != n:
+        raise ValueError("block sizes must sum to the input length")
+    return b, len(b), 0
+
+
+def _nblocks(n: int, block) -> int:
+    if block is None:
+        return 1 if n else 0
+    if np.isscalar(block):
+        return (n + int(block) - 1) // int(block)
+    return len(block)
+
+
+# ---------------------------------------------------------------------------------------------
+# windows (reference src/dsp/window.h)
+# ---------------------------------------------------------------------------------------------
+class generic_window:
+    def getTapCount(self) -> int:  # noqa: N802 (reference naming)
+        raise NotImplementedError
+
+    def createTaps(self, tapCount: int | None = None, factor: float = 1.0) -> np.ndarray:  # noqa: N802
+        raise NotImplementedError
+
+
+class BlackmanWindow(generic_window):
+    """filter_window::BlackmanWindow (window.h:13-76): init(cutoff, transWidth, sampleRate)."""
+
+    def __init__(self, cutoff: float, transWidth: float, sampleRate: float):
+        self.init(cutoff, transWidth, sampleRate)
+
+    def init(self, cutoff, transWidth, sampleRate):
+        self._cutoff, self._transWidth, self._sampleRate = float(cutoff), float(transWidth), float(sampleRate)
+
+    def setSampleRate(self, v):
+        self._sampleRate = float(v)
+
+    def setCutoff(self, v):
+        self._cutoff = float(v)
+
+    def setTransWidth(self, v):
+        self._transWidth = float(v)
+
+    def getTapCount(self) -> int:
+        return int(_L().qdsp_blackman_tap_count(self._cutoff, self._transWidth, self._sampleRate))
+
+    def createTaps(self, tapCount=None, factor=1.0) -> np.ndarray:
+        n = self.getTapCount() if tapCount is None else int(tapCount)
+        t = np.empty(n, np.float32)
+        _L().qdsp_blackman_taps(self._cutoff, self._transWidth, self._sampleRate, _fptr(t), n, float(factor))
+        return t
+
+
+class BlackmanBandpassWindow(BlackmanWindow):
+    """filter_window::BlackmanBandpassWindow (window.h:78-148)."""
+
+    def __init__(self, cutoff, transWidth, offset, sampleRate):
+        self.init(cutoff, transWidth, offset, sampleRate)
+
+    def init(self, cutoff, transWidth, offset, sampleRate):
+        super().init(cutoff, transWidth, sampleRate)
+        self._offset = float(offset)
+
+    def setOffset(self, v):
+        self._offset = float(v)
+
+    def createTaps(self, tapCount=None, factor=1.0) -> np.ndarray:
+        n = self.getTapCount() if tapCount is None else int(tapCount)
+        t = np.empty(n, np.float32)
+        _L().qdsp_blackman_bandpass_taps(self._cutoff, self._transWidth, self._offset, self._sampleRate, _fptr(t), n,
+                                         float(factor))
+        return t
+
+
+class RRCTaps(generic_window):
+    """filter_window::RRCTaps (window.h:150-231): init(tapCount, sampleRate, baudRate, alpha)."""
+
+    def __init__(self, tapCount, sampleRate, baudRate, alpha):
+        self._tapCount, self._sampleRate, self._baudRate, self._alpha = int(tapCount), float(sampleRate), float(baudRate), float(alpha)
+
+    def getTapCount(self) -> int:
+        return self._tapCount
+
+    def createTaps(self, tapCount=None, factor=1.0) -> np.ndarray:
+        n = self._tapCount if tapCount is None else int(tapCount)
+        t = np.zeros(n | 1, np.float32)
+        _L().qdsp_rrc_taps(n, self._sampleRate, self._baudRate, self._alpha, _fptr(t))
+        return t[:n] if n == (n | 1) else t
+
+
+class _TapsWindow(generic_window):
+    """Adapter: a fixed tap vector presented as a window (tests, custom designs)."""
+
+    def __init__(self, taps):
+        self.taps = np.ascontiguousarray(taps, np.float32)
+
+    def getTapCount(self):
+        return len(self.taps)
+
+    def createTaps(self, tapCount=None, factor=1.0):
+        return (self.taps * np.float32(factor)).astype(np.float32)
+
+
+def rates_to_ratio(inSampleRate: float, outSampleRate: float) -> tuple[int, int]:
+    i, d = C.c_int(), C.c_int()
+    _L().qdsp_rates_to_ratio(float(inSampleRate), float(outSampleRate), C.byref(i), C.byref(d))
+    return i.value, d.value
+
+
+def resamp_schedule(interp: int, decim: int, count: int):
+    n = (count * interp) // decim
+    ph, ix = np.empty(n, np.int32), np.empty(n, np.int32)
+    _L().qdsp_resamp_schedule(interp, decim, count, _iptr(ph), _iptr(ix))
+    return ph, ix
+
+
+# ---------------------------------------------------------------------------------------------
+# base class for stream blocks
+# ---------------------------------------------------------------------------------------------
+class _Block:
+    in_dtype = np.complex64
+    out_dtype = np.complex64
+    _destroy = None
+
+    def __init__(self):
+        self.h = None
+        self.stream = None
+
+    def _out_capacity(self, n: int, block) -> int:
+        return n
+
+    def _run(self, in_ptr, out_ptr, n, block):
+        raise NotImplementedError
+
+    def process_device(self, in_ptr, out_ptr, n, block=None, stream=None) -> int:
+        self.stream = stream
+        return int(check(self._run(in_ptr, out_ptr, int(n), block), type(self).__name__))
+
+    def process(self, x, block=None) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=self.in_dtype)
+        n = len(x)
+        din = DevBuf.from_numpy(x)
+        cap = self._out_capacity(n, block)
+        dout = DevBuf(max(cap, 1) * np.dtype(self.out_dtype).itemsize)
+        self.stream = None
+        m = int(check(self._run(din.ptr, dout.ptr, n, block), type(self).__name__))
+        y = dout.to_numpy(self.out_dtype, m)
+        din.free()
+        dout.free()
+        return y
+
+    def close(self):
+        if self.h and self._destroy:
+            getattr(_L(), self._destroy)(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------------------------------
+# FIR / resampling (reference filter.h, resampling.h)
+# ---------------------------------------------------------------------------------------------
+class FIR(_Block):
+    """dsp::FIR<T>: init(in, window). `dtype` is np.complex64 (complex_t) or np.float32."""
+
+    _destroy = "qdsp_fir_destroy"
+
+    def __init__(self, window: generic_window, dtype=np.complex64):
+        super().__init__()
+        _lib.require_device()
+        self.in_dtype = self.out_dtype = np.dtype(dtype).type
+        self.taps = window.createTaps(window.getTapCount())
+        kind = CF32 if self.in_dtype is np.complex64 else F32
+        self.h = check(_L().qdsp_fir_create(kind, _fptr(self.taps), len(self.taps)), "qdsp_fir_create")
+
+    def updateWindow(self, window: generic_window):  # noqa: N802
+        self.taps = window.createTaps(window.getTapCount())
+        check(_L().qdsp_fir_set_taps(self.h, _fptr(self.taps), len(self.taps)), "qdsp_fir_set_taps")
+
+    def set_variant(self, v: int):
+        _L().qdsp_fir_set_variant(self.h, v)
+
+    def history_len(self) -> int:
+        return _L().qdsp_fir_history_len(self.h)
+
+    def import_tail(self, tail_ptr, src_device=-1, stream=None):
+        check(_L().qdsp_fir_import_tail(self.h, tail_ptr, src_device, stream), "qdsp_fir_import_tail")
+
+    def set_history(self, hist: np.ndarray):
+        hist = np.ascontiguousarray(hist, self.in_dtype)
+        assert len(hist) == self.history_len()
+        check(_L().qdsp_fir_set_history(self.h, hist.ctypes.data), "qdsp_fir_set_history")
+
+    def get_history(self) -> np.ndarray:
+        out = np.empty(self.history_len(), self.in_dtype)
+        check(_L().qdsp_fir_get_history(self.h, out.ctypes.data), "qdsp_fir_get_history")
+        return out
+
+    def reset(self):
+        check(_L().qdsp_fir_reset(self.h))
+
+    def _run(self, in_ptr, out_ptr, n, block):
+        return _L().qdsp_fir_process(self.h, in_ptr, out_ptr, n, self.stream)
+
+
+class PolyphaseResampler(_Block):
+    """dsp::PolyphaseResampler<T>: init(in, window, inSampleRate, outSampleRate)."""
+
+    _destroy = "qdsp_resamp_destroy"
+
+    def __init__(self, window: generic_window, inSampleRate: float, outSampleRate: float, dtype=np.complex64):
+        super().__init__()
+        _lib.require_device()
+        self.in_dtype = self.out_dtype = np.dtype(dtype).type
+        self._interp, self._decim = rates_to_ratio(inSampleRate, outSampleRate)
+        self.taps = window.createTaps(window.getTapCount(), float(self._interp))
+        kind = CF32 if self.in_dtype is np.complex64 else F32
+        self.h = check(_L().qdsp_resamp_create(kind, _fptr(self.taps), len(self.taps), self._interp, self._decim),
+                       "qdsp_resamp_create")
+        self.last_out_counts = None
+
+    def getInterpolation(self):  # noqa: N802
+        return self._interp
+
+    def getDecimation(self):  # noqa: N802
+        return self._decim
+
+    def updateWindow(self, window: generic_window):  # noqa: N802
+        self.taps = window.createTaps(window.getTapCount(), float(self._interp))
+        check(_L().qdsp_resamp_set_taps(self.h, _fptr(self.taps), len(self.taps)), "qdsp_resamp_set_taps")
+
+    def calcOutSize(self, n: int) -> int:  # noqa: N802
+        return int(_L().qdsp_resamp_out_count(self.h, n))
+
+    def tapsPerPhase(self) -> int:  # noqa: N802
+        return _L().qdsp_resamp_taps_per_phase(self.h)
+
+    def set_variant(self, v: int):
+        _L().qdsp_resamp_set_variant(self.h, v)
+
+    def reset(self):
+        check(_L().qdsp_resamp_reset(self.h))
+
+    def _out_capacity(self, n, block):
+        return (n * self._interp) // self._decim + 16
+
+    def _run(self, in_ptr, out_ptr, n, block):
+        b, nb, bs = _blocks_arg(n, block)
+        oc = np.zeros(max(_nblocks(n, block), 1), np.int32)
+        r = _L().qdsp_resamp_process(self.h, in_ptr, out_ptr, n, _iptr(b), nb, bs, _iptr(oc), self.stream)
+        self.last_out_counts = oc[: _nblocks(n, block)]
+        return r
+
+    def schedule_device(self, n: int, block=None):
+        """(phase, index) of every output as computed on the device."""
+        b, nb, bs = _blocks_arg(n, block)
+        cap = self._out_capacity(n, block)
+        dp, di = DevBuf(cap * 4), DevBuf(cap * 8)
+        m = int(check(_L().qdsp_resamp_schedule_device(self.h, n, _iptr(b), nb, bs, dp.ptr, di.ptr, None)))
+        return dp.to_numpy(np.int32, m), di.to_numpy(np.int64, m)
+
+
+class PowerDecimator(_Block):
+    """dsp::PowerDecimator: init(in, power)."""
+
+    def __init__(self, power: int):
+        super().__init__()
+        _lib.require_device()
+        self._power = int(power)
+
+    def setPower(self, power):  # noqa: N802
+        self._power = int(power)
+
+    def _run(self, in_ptr, out_ptr, n, block):
+        return _L().qdsp_power_decim_process(self._power, in_ptr, out_ptr, n, self.stream)
+
+
+# ---------------------------------------------------------------------------------------------
+# processing / demodulation (reference processing.h, demodulator.h, vfo.h)
+# ---------------------------------------------------------------------------------------------
+class FrequencyXlator(_Block):
+    """dsp::FrequencyXlator<complex_t>: init(in, sampleRate, freq)."""
+
+    _destroy = "qdsp_xlator_destroy"
+
+    def __init__(self, sampleRate: float, freq: float):
+        super().__init__()
+        _lib.require_device()
+        self._sampleRate, self._freq = float(sampleRate), float(freq)
+        self.h = check(_L().qdsp_xlator_create(self._sampleRate, self._freq), "qdsp_xlator_create")
+
+    def setSampleRate(self, v):  # noqa: N802
+        self._sampleRate = float(v)
+        _L().qdsp_xlator_set_frequency(self.h, self._sampleRate, self._freq)
+
+    def setFrequency(self, v):  # noqa: N802
+        self._freq = float(v)
+        _L().qdsp_xlator_set_frequency(self.h, self._sampleRate, self._freq)
+
+    def getFrequency(self):  # noqa: N802
+        return self._freq
+
+    def phase_delta(self) -> complex:
+        re, im = C.c_float(), C.c_float()
+        _L().qdsp_xlator_get_phase_delta(self.h, C.byref(re), C.byref(im))
+        return complex(re.value, im.value)
+
+    def get_phase(self) -> complex:
+        re, im = C.c_float(), C.c_float()
+        _L().qdsp_xlator_get_phase(self.h, C.byref(re), C.byref(im))
+        return complex(re.value, im.value)
+
+    def set_phase(self, p: complex):
+        _L().qdsp_xlator_set_phase(self.h, float(p.real), float(p.imag))
+
+    def _run(self, in_ptr, out_ptr, n, block):
+        return _L().qdsp_xlator_process(self.h, in_ptr, out_ptr, n, self.stream)
+
+
+class FloatFMDemod(_Block):
+    """dsp::FloatFMDemod: init(in, sampleRate, deviation) -> float audio."""
+
+    _destroy = "qdsp_fmdemod_destroy"
+    out_dtype = np.float32
+    _stereo = 0
+
+    def __init__(self, sampleRate: float, deviation: float):
+        super().__init__()
+        _lib.require_device()
+        self.h = check(_L().qdsp_fmdemod_create(float(sampleRate), float(deviation), self._stereo))
+
+    def get_phase(self) -> float:
+        return float(_L().qdsp_fmdemod_get_phase(self.h))
+
+    def set_phase(self, v: float):
+        check(_L().qdsp_fmdemod_set_phase(self.h, float(v)))
+
+    def _run(self, in_ptr, out_ptr, n, block):
+        return _L().qdsp_fmdemod_process(self.h, in_ptr, out_ptr, n, self.stream)
+
+
+class FMDemod(FloatFMDemod):
+    """dsp::FMDemod: same demodulator writing stereo_t {l = r = audio} (viewed as complex64)."""
+
+    out_dtype = np.complex64
+    _stereo = 1
+
+
+class VFO:
+    """dsp::VFO (vfo.h): FrequencyXlator(-offset) -> PolyphaseResampler with the auto-designed window,
+    run block by block as two kernels (the unfused composition; `VFOFM` is the fused pass)."""
+
+    def __init__(self, offset, inSampleRate, outSampleRate, bandWidth):
+        self.init(offset, inSampleRate, outSampleRate, bandWidth)
+
+    def init(self, offset, inSampleRate, outSampleRate, bandWidth):
+        self._offset, self._in, self._out, self._bw = float(offset), float(inSampleRate), float(outSampleRate), float(bandWidth)
+        cutoff = min(self._bw, min(self._in, self._out)) / 2.0
+        self.xlator = FrequencyXlator(self._in, -self._offset)
+        self.win = BlackmanWindow(cutoff, cutoff, self._in)
+        interp, _ = rates_to_ratio(self._in, self._out)
+        self.win.setSampleRate(np.float32(self._in) * np.float32(interp))
+        self.resamp = PolyphaseResampler(self.win, self._in, self._out)
+
+    def setOffset(self, offset):  # noqa: N802
+        self._offset = float(offset)
+        self.xlator.setFrequency(-self._offset)
+
+    def process(self, x, block=None) -> np.ndarray:
+        x = np.ascontiguousarray(x, np.complex64)
+        return self.resamp.process(self.xlator.process(x), block)
+
+
+class VFOFM(_Block):
+    """Fused VFO -> FloatFMDemod (one kernel; translated and resampled IQ stay on chip)."""
+
+    _destroy = "qdsp_vfofm_destroy"
+    out_dtype = np.float32
+
+    def __init__(self, offset, inSampleRate, outSampleRate, bandWidth, deviation):
+        super().__init__()
+        _lib.require_device()
+        self.h = check(_L().qdsp_vfofm_create(float(offset), float(inSampleRate), float(outSampleRate),
+                                              float(bandWidth), float(deviation)), "qdsp_vfofm_create")
+        t, i, d = C.c_int(), C.c_int(), C.c_int()
+        _L().qdsp_vfofm_design(self.h, C.byref(t), C.byref(i), C.byref(d))
+        self.tapCount, self._interp, self._decim = t.value, i.value, d.value
+        self.want_iq = False
+        self.last_iq = None
+        self.last_out_counts = None
+
+    def setOffset(self, offset):  # noqa: N802
+        check(_L().qdsp_vfofm_set_offset(self.h, float(offset)))
+
+    def set_variant(self, v: int):
+        _L().qdsp_vfofm_set_variant(self.h, v)
+
+    def reset(self):
+        check(_L().qdsp_vfofm_reset(self.h))
+
+    def seek(self, start: int):
+        check(_L().qdsp_vfofm_seek(self.h, int(start)))
+
+    def history_len(self) -> int:
+        return _L().qdsp_vfofm_history_len(self.h)
+
+    def import_tail(self, tail_ptr, src_device=-1, stream=None):
+        check(_L().qdsp_vfofm_import_tail(self.h, tail_ptr, src_device, stream))
+
+    def out_count(self, n, block=None) -> int:
+        b, nb, bs = _blocks_arg(n, block)
+        return int(check(_L().qdsp_vfofm_out_count(self.h, n, _iptr(b), nb, bs)))
+
+    def _out_capacity(self, n, block):
+        return (n * self._interp) // self._decim + 16
+
+    def _run(self, in_ptr, out_ptr, n, block, iq_ptr=None):
+        b, nb, bs = _blocks_arg(n, block)
+        oc = np.zeros(max(_nblocks(n, block), 1), np.int32)
+        r = _L().qdsp_vfofm_process(self.h, in_ptr, out_ptr, iq_ptr, n, _iptr(b), nb, bs, _iptr(oc), self.stream)
+        self.last_out_counts = oc[: _nblocks(n, block)]
+        return r
+
+    def process(self, x, block=None) -> np.ndarray:
+        if not self.want_iq:
+            return super().process(x, block)
+        x = np.ascontiguousarray(x, np.complex64)
+        n = len(x)
+        din = DevBuf.from_numpy(x)
+        cap = self._out_capacity(n, block)
+        dout, diq = DevBuf(cap * 4), DevBuf(cap * 8)
+        self.stream = None
+        m = int(check(self._run(din.ptr, dout.ptr, n, block, diq.ptr), "VFOFM"))
+        self.last_iq = diq.to_numpy(np.complex64, m)
+        return dout.to_numpy(np.float32, m)
+
+    def process_host(self, x: np.ndarray, out: np.ndarray, block_size: int, stream=None) -> int:
+        """End-to-end call with HOST buffers (pinned for real overlap): chunked H2D/compute/D2H inside."""
+        return int(check(_L().qdsp_vfofm_process_host(self.h, x.ctypes.data, out.ctypes.data, len(x), int(block_size),
+                                                      stream), "qdsp_vfofm_process_host"))
+
+
+class Channelizer(_Block):
+    """nch x [VFO -> FloatFMDemod] fed by one Splitter (routing.h:47-57): every channel reads the same
+    device-resident wideband buffer; output is [nch, n_out] float32."""
+
+    _destroy = "qdsp_channelizer_destroy"
+    out_dtype = np.float32
+
+    def __init__(self, offsets, inSampleRate, outSampleRate, bandWidth, deviation):
+        super().__init__()
+        _lib.require_device()
+        self.offsets = np.ascontiguousarray(offsets, np.float32)
+        self.nch = len(self.offsets)
+        self.h = check(_L().qdsp_channelizer_create(self.nch, _fptr(self.offsets), float(inSampleRate),
+                                                    float(outSampleRate), float(bandWidth), float(deviation)))
+        t, i, d = C.c_int(), C.c_int(), C.c_int()
+        _L().qdsp_channelizer_design(self.h, C.byref(t), C.byref(i), C.byref(d))
+        self.tapCount, self._interp, self._decim = t.value, i.value, d.value
+
+    def set_variant(self, v: int):
+        _L().qdsp_channelizer_set_variant(self.h, v)
+
+    def reset(self):
+        check(_L().qdsp_channelizer_reset(self.h))
+
+    def process_device(self, in_ptr, out_ptr, n, out_stride, block=None, stream=None) -> int:
+        b, nb, bs = _blocks_arg(n, block)
+        return int(check(_L().qdsp_channelizer_process(self.h, in_ptr, out_ptr, int(out_stride), int(n), _iptr(b), nb,
+                                                       bs, stream), "qdsp_channelizer_process"))
+
+    def process(self, x, block=None) -> np.ndarray:
+        x = np.ascontiguousarray(x, np.complex64)
+        n = len(x)
+        stride = (n * self._interp) // self._decim + 16
+        din, dout = DevBuf.from_numpy(x), DevBuf(self.nch * stride * 4)
+        m = self.process_device(din.ptr, dout.ptr, n, stride, block)
+        y = dout.to_numpy(np.float32, self.nch * stride).reshape(self.nch, stride)[:, :m].copy()
+        return y
+
+
+# ---------------------------------------------------------------------------------------------
+# recurrent blocks (reference filter.h BFMDeemp, processing.h AGCs, pll.h CostasLoop)
+# ---------------------------------------------------------------------------------------------
+class BFMDeemp(_Block):
+    """dsp::BFMDeemp: init(in, sampleRate, tau); stereo_t stream viewed as complex64 (l=re, r=im)."""
+
+    _destroy = "qdsp_deemp_destroy"
+
+    def __init__(self, sampleRate, tau):
+        super().__init__()
+        _lib.require_device()
+        self.h = check(_L().qdsp_deemp_create(float(sampleRate), float(tau)))
+
+    def get_state(self):
+        l, r = C.c_float(), C.c_float()
+        check(_L().qdsp_deemp_get_state(self.h, C.byref(l), C.byref(r)))
+        return l.value, r.value
+
+    def set_state(self, l, r):
+        check(_L().qdsp_deemp_set_state(self.h, float(l), float(r)))
+
+    def _run(self, in_ptr, out_ptr, n, block):
+        return _L().qdsp_deemp_process(self.h, in_ptr, out_ptr, n, self.stream)
+
+
+class AGC(_Block):
+    """dsp::AGC: init(in, fallRate, sampleRate); float stream; result depends on the run() partition."""
+
+    _destroy = "qdsp_agc_destroy"
+    in_dtype = np.float32
+    out_dtype = np.float32
+
+    def __init__(self, fallRate, sampleRate):
+        super().__init__()
+        _lib.require_device()
+        self.h = check(_L().qdsp_agc_create(float(fallRate), float(sampleRate)))
+
+    def get_state(self) -> float:
+        v = C.c_float()
+        check(_L().qdsp_agc_get_state(self.h, C.byref(v)))
+        return v.value
+
+    def _run(self, in_ptr, out_ptr, n, block):
+        b, nb, bs = _blocks_arg(n, block)
+        return _L().qdsp_agc_process(self.h, in_ptr, out_ptr, n, _iptr(b), nb, bs, self.stream)
+
+
+class ComplexAGC(_Block):
+    """dsp::ComplexAGC: init(in, setPoint, maxGain, rate)."""
+
+    _destroy = "qdsp_cagc_destroy"
+
+    def __init__(self, setPoint, maxGain, rate):
+        super().__init__()
+        _lib.require_device()
+        self.h = check(_L().qdsp_cagc_create(float(setPoint), float(maxGain), float(rate)))
+
+    def get_state(self) -> float:
+        v = C.c_float()
+        check(_L().qdsp_cagc_get_state(self.h, C.byref(v)))
+        return v.value
+
+    def set_state(self, g):
+        check(_L().qdsp_cagc_set_state(self.h, float(g)))
+
+    def _run(self, in_ptr, out_ptr, n, block):
+        return _L().qdsp_cagc_process(self.h, in_ptr, out_ptr, n, self.stream)
+
+
+class FeedForwardAGC(_Block):
+    """dsp::FeedForwardAGC<T>: init(in); returns the valid (toProcess) outputs of each call."""
+
+    _destroy = "qdsp_ffagc_destroy"
+
+    def __init__(self, dtype=np.complex64):
+        super().__init__()
+        _lib.require_device()
+        self.in_dtype = self.out_dtype = np.dtype(dtype).type
+        self.h = check(_L().qdsp_ffagc_create(CF32 if self.in_dtype is np.complex64 else F32))
+
+    def _run(self, in_ptr, out_ptr, n, block):
+        return _L().qdsp_ffagc_process(self.h, in_ptr, out_ptr, n, self.stream)
+
+
+class CostasLoop(_Block):
+    """dsp::CostasLoop<ORDER>: init(in, loopBandwidth)."""
+
+    _destroy = "qdsp_costas_destroy"
+
+    def __init__(self, order: int, loopBandwidth: float):
+        super().__init__()
+        _lib.require_device()
+        self.h = check(_L().qdsp_costas_create(int(order), float(loopBandwidth)))
+
+    def set_chunking(self, chunk: int, warmup: int):
+        _L().qdsp_costas_set_chunking(self.h, int(chunk), int(warmup))
+
+    def get_state(self) -> np.ndarray:
+        st = np.zeros(4, np.float32)
+        check(_L().qdsp_costas_get_state(self.h, _fptr(st)))
+        return st
+
+    def set_state(self, st):
+        st = np.ascontiguousarray(st, np.float32)
+        check(_L().qdsp_costas_set_state(self.h, _fptr(st)))
+
+    def last_residual(self) -> float:
+        return float(_L().qdsp_costas_last_residual(self.h))
+
+    def _run(self, in_ptr, out_ptr, n, block):
+        return _L().qdsp_costas_process(self.h, in_ptr, out_ptr, n, self.stream)
+
+
+__all__ = [n for n in dir() if not n.startswith("_")]

@@ -1,0 +1,879 @@
+// qdsp_b200/csrc/api.cu — the C ABI (include/qdsp_b200.h): opaque handles, state, dispatch.
+// No compute happens on the host; every process call enqueues sm_100a kernels on the caller's stream.
+#include <math.h>
+#include <string.h>
+#include <new>
+#include <vector>
+#include "internal.cuh"
+#include "kernels.cuh"
+
+using namespace qdsp;
+
+namespace {
+
+// taps -> polyphase bank, reference src/dsp/resampling.h:137-166 (buildTapPhases):
+// tapsPerPhase = ceil(tapCount / interp); phases[(I-1)-p][t] = taps[t*I + p], zero padded.
+std::vector<float> build_phases(const float* taps, int T, int interp, int* tpp_out) {
+    const int tpp = (T + interp - 1) / interp;
+    std::vector<float> ph((size_t)interp * tpp, 0.0f);
+    for (int p = 0; p < interp; p++)
+        for (int t = 0; t < tpp; t++) {
+            const int idx = t * interp + p;
+            ph[(size_t)(interp - 1 - p) * tpp + t] = idx < T ? taps[idx] : 0.0f;
+        }
+    *tpp_out = tpp;
+    return ph;
+}
+
+int upload_floats(float** dev, const std::vector<float>& v) {
+    if (*dev) cudaFree(*dev);
+    *dev = nullptr;
+    QDSP_CUDA_OK(cudaMalloc(dev, sizeof(float) * (v.size() + 16)));
+    QDSP_CUDA_OK(cudaMemset(*dev, 0, sizeof(float) * (v.size() + 16)));
+    QDSP_CUDA_OK(cudaMemcpy(*dev, v.data(), sizeof(float) * v.size(), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+struct Scratch {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        QDSP_CUDA_OK(cudaMalloc(&p, bytes));
+        cap = bytes;
+        return 0;
+    }
+    ~Scratch() {
+        if (p) cudaFree(p);
+    }
+};
+
+// small device-resident float state with host get/set
+struct DevState {
+    float* p = nullptr;
+    int n = 0;
+    int init(int n_, const float* v) {
+        n = n_;
+        QDSP_CUDA_OK(cudaMalloc(&p, sizeof(float) * n));
+        QDSP_CUDA_OK(cudaMemcpy(p, v, sizeof(float) * n, cudaMemcpyHostToDevice));
+        return 0;
+    }
+    int get(float* v, int count, int offset = 0) const {
+        QDSP_CUDA_OK(cudaDeviceSynchronize());
+        QDSP_CUDA_OK(cudaMemcpy(v, p + offset, sizeof(float) * count, cudaMemcpyDeviceToHost));
+        return 0;
+    }
+    int set(const float* v, int count, int offset = 0) {
+        QDSP_CUDA_OK(cudaDeviceSynchronize());
+        QDSP_CUDA_OK(cudaMemcpy(p + offset, v, sizeof(float) * count, cudaMemcpyHostToDevice));
+        return 0;
+    }
+    ~DevState() {
+        if (p) cudaFree(p);
+    }
+};
+
+int import_tail_impl(History& hist, const void* tail_dev, int src_device, cudaStream_t s) {
+    if (hist.H <= 0) return 0;
+    int dev = 0;
+    QDSP_CUDA_OK(cudaGetDevice(&dev));
+    const size_t bytes = (size_t)hist.H * hist.elem;
+    if (src_device < 0 || src_device == dev)
+        QDSP_CUDA_OK(cudaMemcpyAsync(hist.buf[hist.cur], tail_dev, bytes, cudaMemcpyDeviceToDevice, s));
+    else
+        QDSP_CUDA_OK(cudaMemcpyPeerAsync(hist.buf[hist.cur], dev, tail_dev, src_device, bytes, s));
+    return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+// FIR
+// =================================================================================================
+struct qdsp_fir {
+    int dtype = QDSP_CF32;
+    int T = 0;
+    float* taps_dev = nullptr;  // phases layout for I=1 == taps
+    History hist;
+    Partition part;
+    FirPlan* plan = nullptr;
+    int variant = 0;
+    std::vector<float> taps;
+};
+
+extern "C" {
+
+qdsp_fir* qdsp_fir_create(int dtype, const float* taps, int tapCount) {
+    if (!taps || tapCount <= 0 || (dtype != QDSP_F32 && dtype != QDSP_CF32)) {
+        set_last_error("fir_create: bad arguments");
+        return nullptr;
+    }
+    qdsp_fir* h = new (std::nothrow) qdsp_fir();
+    if (!h) return nullptr;
+    h->dtype = dtype;
+    if (qdsp_fir_set_taps(h, taps, tapCount) != 0) {
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+void qdsp_fir_destroy(qdsp_fir* h) {
+    if (!h) return;
+    if (h->taps_dev) cudaFree(h->taps_dev);
+    if (h->plan) fir_plan_destroy(h->plan);
+    h->hist.release();
+    delete h;
+}
+int qdsp_fir_set_taps(qdsp_fir* h, const float* taps, int tapCount) {
+    h->taps.assign(taps, taps + tapCount);
+    if (upload_floats(&h->taps_dev, h->taps) != 0) return -1;
+    if (tapCount != h->T) {
+        h->T = tapCount;
+        // reference filter.h:28 leaves the history uninitialised; we define it as zeros
+        if (h->hist.init(tapCount - 1, h->dtype == QDSP_CF32 ? 8 : 4) != 0) return -1;
+    }
+    if (h->plan) fir_plan_destroy(h->plan);
+    h->plan = (h->dtype == QDSP_CF32) ? fir_plan_create(taps, tapCount) : nullptr;
+    return 0;
+}
+long long qdsp_fir_process(qdsp_fir* h, const void* in_dev, void* out_dev, long long count, qdsp_stream_t s_) {
+    cudaStream_t s = as_stream(s_);
+    if (count < 0) return -1;
+    if (count == 0) return 0;
+    const bool dense = h->plan && h->variant != 1;
+    if (dense) {
+        if (launch_fir_dense(h->plan, (const float2*)h->hist.ptr(), h->hist.H, (const float2*)in_dev, count, 1,
+                             (float2*)out_dev, s) != 0)
+            return -1;
+    } else {
+        // FIR == polyphase bank with I = D = 1 read one sample later (filter.h:65 reads &buffer[i+1]);
+        // y[i] = sum_j taps[j] * x[i - (T-1) + j]; the generic kernel's TPP-deep window with lead=1.
+        // Blocks of <= 2^30 outputs keep per-block counts in int.
+        if (h->part.build(count, nullptr, 0, 1 << 20, 1, 1, s) != 0) return -1;
+        int rc;
+        // history is T-1 deep; the generic kernel's virtual stream tolerates reads one element
+        // further back (returns 0 there, multiplied by no tap: base index starts at -(T-1)).
+        if (h->dtype == QDSP_CF32)
+            rc = launch_generic_resamp<float2>((const float2*)h->hist.ptr(), h->hist.H, (const float2*)in_dev,
+                                               h->taps_dev, h->T, 1, h->part, (float2*)out_dev, s);
+        else
+            rc = launch_generic_resamp<float>((const float*)h->hist.ptr(), h->hist.H, (const float*)in_dev,
+                                              h->taps_dev, h->T, 1, h->part, (float*)out_dev, s);
+        if (rc != 0) return -1;
+    }
+    if (h->hist.advance(in_dev, count, s) != 0) return -1;
+    return count;
+}
+int qdsp_fir_history_len(qdsp_fir* h) { return h->hist.H; }
+int qdsp_fir_get_history(qdsp_fir* h, void* hist_host) {
+    QDSP_CUDA_OK(cudaDeviceSynchronize());
+    if (h->hist.H > 0)
+        QDSP_CUDA_OK(cudaMemcpy(hist_host, h->hist.ptr(), (size_t)h->hist.H * h->hist.elem, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int qdsp_fir_set_history(qdsp_fir* h, const void* hist_host) {
+    QDSP_CUDA_OK(cudaDeviceSynchronize());
+    if (h->hist.H > 0)
+        QDSP_CUDA_OK(cudaMemcpy(h->hist.buf[h->hist.cur], hist_host, (size_t)h->hist.H * h->hist.elem,
+                                cudaMemcpyHostToDevice));
+    return 0;
+}
+int qdsp_fir_import_tail(qdsp_fir* h, const void* tail_dev, int src_device, qdsp_stream_t s) {
+    return import_tail_impl(h->hist, tail_dev, src_device, as_stream(s));
+}
+int qdsp_fir_reset(qdsp_fir* h) { return h->hist.reset(nullptr); }
+int qdsp_fir_set_variant(qdsp_fir* h, int variant) {
+    h->variant = variant;
+    return 0;
+}
+
+}  // extern "C"
+
+// =================================================================================================
+// PolyphaseResampler
+// =================================================================================================
+struct qdsp_resamp {
+    int dtype = QDSP_CF32;
+    int T = 0, interp = 1, decim = 1, tpp = 0;
+    float* phases_dev = nullptr;
+    History hist;
+    Partition part;
+    DecimPlan* plan = nullptr;
+    int variant = 0;
+};
+
+extern "C" {
+
+qdsp_resamp* qdsp_resamp_create(int dtype, const float* taps, int tapCount, int interp, int decim) {
+    if (!taps || tapCount <= 0 || interp <= 0 || decim <= 0 || (dtype != QDSP_F32 && dtype != QDSP_CF32)) {
+        set_last_error("resamp_create: bad arguments");
+        return nullptr;
+    }
+    qdsp_resamp* h = new (std::nothrow) qdsp_resamp();
+    if (!h) return nullptr;
+    h->dtype = dtype;
+    h->interp = interp;
+    h->decim = decim;
+    if (qdsp_resamp_set_taps(h, taps, tapCount) != 0) {
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+void qdsp_resamp_destroy(qdsp_resamp* h) {
+    if (!h) return;
+    if (h->phases_dev) cudaFree(h->phases_dev);
+    if (h->plan) decim_plan_destroy(h->plan);
+    h->hist.release();
+    delete h;
+}
+int qdsp_resamp_set_taps(qdsp_resamp* h, const float* taps, int tapCount) {
+    int tpp = 0;
+    std::vector<float> ph = build_phases(taps, tapCount, h->interp, &tpp);
+    if (upload_floats(&h->phases_dev, ph) != 0) return -1;
+    h->T = tapCount;
+    if (tpp != h->tpp) {
+        h->tpp = tpp;
+        if (h->hist.init(tpp, h->dtype == QDSP_CF32 ? 8 : 4) != 0) return -1;  // zeroed, resampling.h:39
+    }
+    if (h->plan) decim_plan_destroy(h->plan);
+    h->plan = nullptr;
+    if (h->dtype == QDSP_CF32 && decim_plan_supported(tapCount, h->interp, h->decim))
+        h->plan = decim_plan_create(taps, tapCount, h->decim);
+    return 0;
+}
+int qdsp_resamp_taps_per_phase(qdsp_resamp* h) { return h->tpp; }
+long long qdsp_resamp_out_count(qdsp_resamp* h, long long count) { return (count * h->interp) / h->decim; }
+
+long long qdsp_resamp_process(qdsp_resamp* h, const void* in_dev, void* out_dev, long long count, const int* blocks,
+                              int nblocks, int block_size, int* out_counts, qdsp_stream_t s_) {
+    cudaStream_t s = as_stream(s_);
+    if (h->part.build(count, blocks, nblocks, block_size, h->interp, h->decim, s) != 0) return -1;
+    if (out_counts) {
+        for (int b = 0; b < h->part.view.nblocks; b++) {
+            if (blocks) out_counts[b] = h->part.host[b].out_count;
+            else {
+                const long long st = (long long)b * h->part.view.block_size;
+                const long long c = count - st < h->part.view.block_size ? count - st : h->part.view.block_size;
+                out_counts[b] = (int)((c * h->interp) / h->decim);
+            }
+        }
+    }
+    if (count == 0) return 0;
+    int rc;
+    if (h->plan && h->variant != 1) {
+        rc = launch_decim(h->plan, (const float2*)h->hist.ptr(), h->hist.H, (const float2*)in_dev, h->part, 0, nullptr,
+                          0, 1, 0.0f, nullptr, nullptr, (float2*)out_dev, nullptr, 0, s);
+    } else if (h->dtype == QDSP_CF32) {
+        rc = launch_generic_resamp<float2>((const float2*)h->hist.ptr(), h->hist.H, (const float2*)in_dev,
+                                           h->phases_dev, h->tpp, 0, h->part, (float2*)out_dev, s);
+    } else {
+        rc = launch_generic_resamp<float>((const float*)h->hist.ptr(), h->hist.H, (const float*)in_dev, h->phases_dev,
+                                          h->tpp, 0, h->part, (float*)out_dev, s);
+    }
+    if (rc != 0) return -1;
+    if (h->hist.advance(in_dev, count, s) != 0) return -1;
+    return h->part.total_out;
+}
+long long qdsp_resamp_schedule_device(qdsp_resamp* h, long long count, const int* blocks, int nblocks, int block_size,
+                                      int* phase_dev, long long* index_dev, qdsp_stream_t s_) {
+    cudaStream_t s = as_stream(s_);
+    if (h->part.build(count, blocks, nblocks, block_size, h->interp, h->decim, s) != 0) return -1;
+    if (launch_schedule(h->part, phase_dev, index_dev, s) != 0) return -1;
+    return h->part.total_out;
+}
+int qdsp_resamp_history_len(qdsp_resamp* h) { return h->hist.H; }
+int qdsp_resamp_get_history(qdsp_resamp* h, void* hist_host) {
+    QDSP_CUDA_OK(cudaDeviceSynchronize());
+    QDSP_CUDA_OK(cudaMemcpy(hist_host, h->hist.ptr(), (size_t)h->hist.H * h->hist.elem, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int qdsp_resamp_set_history(qdsp_resamp* h, const void* hist_host) {
+    QDSP_CUDA_OK(cudaDeviceSynchronize());
+    QDSP_CUDA_OK(cudaMemcpy(h->hist.buf[h->hist.cur], hist_host, (size_t)h->hist.H * h->hist.elem,
+                            cudaMemcpyHostToDevice));
+    return 0;
+}
+int qdsp_resamp_reset(qdsp_resamp* h) { return h->hist.reset(nullptr); }
+int qdsp_resamp_set_variant(qdsp_resamp* h, int variant) {
+    h->variant = variant;
+    return 0;
+}
+
+// =================================================================================================
+// PowerDecimator (stateless) — reference resampling.h:220-249, including the power>1 quirk: the
+// extra passes re-read the input, so the result is the first count>>(power-1) pair averages.
+// =================================================================================================
+long long qdsp_power_decim_process(unsigned int power, const void* in_dev, void* out_dev, long long count,
+                                   qdsp_stream_t s) {
+    if (count < 0) return -1;
+    long long n_out;
+    if (power == 0) n_out = count;
+    else if (power == 1) n_out = count / 2;
+    else n_out = power - 1 >= 62 ? 0 : (count >> (power - 1));
+    if (launch_power_decim((const float2*)in_dev, (float2*)out_dev, n_out, power == 0, as_stream(s)) != 0) return -1;
+    return n_out;
+}
+
+}  // extern "C"
+
+// =================================================================================================
+// FrequencyXlator
+// =================================================================================================
+struct qdsp_xlator {
+    Nco nco;
+    float2 inc_pow[3];
+    void refresh() {
+        const double th = atan2((double)nco.inc_im, (double)nco.inc_re);
+        for (int j = 1; j <= 3; j++) inc_pow[j - 1] = make_float2((float)cos(th * j), (float)sin(th * j));
+    }
+};
+
+extern "C" {
+
+qdsp_xlator* qdsp_xlator_create(float sampleRate, float freq) {
+    qdsp_xlator* h = new (std::nothrow) qdsp_xlator();
+    if (!h) return nullptr;
+    h->nco.set_freq(sampleRate, freq);
+    h->nco.phase = 0;  // phase = (1, 0), processing.h:20
+    h->refresh();
+    return h;
+}
+void qdsp_xlator_destroy(qdsp_xlator* h) { delete h; }
+int qdsp_xlator_set_frequency(qdsp_xlator* h, float sampleRate, float freq) {
+    h->nco.set_freq(sampleRate, freq);
+    h->refresh();
+    return 0;
+}
+void qdsp_xlator_get_phase_delta(qdsp_xlator* h, float* re, float* im) {
+    *re = h->nco.inc_re;
+    *im = h->nco.inc_im;
+}
+void qdsp_xlator_get_phase(qdsp_xlator* h, float* re, float* im) { h->nco.get_phase(re, im); }
+void qdsp_xlator_set_phase(qdsp_xlator* h, float re, float im) { h->nco.set_phase(re, im); }
+long long qdsp_xlator_process(qdsp_xlator* h, const void* in_dev, void* out_dev, long long count, qdsp_stream_t s) {
+    if (count < 0) return -1;
+    if (launch_xlator((const float2*)in_dev, (float2*)out_dev, count, h->nco.phase, h->nco.step, h->inc_pow[0],
+                      h->inc_pow[1], h->inc_pow[2], as_stream(s)) != 0)
+        return -1;
+    h->nco.advance(count);
+    return count;
+}
+
+}  // extern "C"
+
+// =================================================================================================
+// FloatFMDemod / FMDemod
+// =================================================================================================
+struct qdsp_fmdemod {
+    float phasor_speed = 1.0f;
+    int stereo = 0;
+    DevState st;  // [2] ping-pong
+    int cur = 0;
+};
+
+static float fm_phasor_speed(float sampleRate, float deviation) {
+    return (2 * QDSP_FL_M_PI) / (sampleRate / deviation);  // demodulator.h:43
+}
+
+extern "C" {
+
+qdsp_fmdemod* qdsp_fmdemod_create(float sampleRate, float deviation, int stereo_out) {
+    qdsp_fmdemod* h = new (std::nothrow) qdsp_fmdemod();
+    if (!h) return nullptr;
+    h->phasor_speed = fm_phasor_speed(sampleRate, deviation);
+    h->stereo = stereo_out;
+    const float z[2] = {0.0f, 0.0f};
+    if (h->st.init(2, z) != 0) {
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+void qdsp_fmdemod_destroy(qdsp_fmdemod* h) { delete h; }
+float qdsp_fmdemod_get_phase(qdsp_fmdemod* h) {
+    float v = 0.0f;
+    h->st.get(&v, 1, h->cur);
+    return v;
+}
+int qdsp_fmdemod_set_phase(qdsp_fmdemod* h, float phase) { return h->st.set(&phase, 1, h->cur); }
+long long qdsp_fmdemod_process(qdsp_fmdemod* h, const void* in_dev, void* out_dev, long long count, qdsp_stream_t s) {
+    if (count < 0) return -1;
+    if (count == 0) return 0;
+    if (launch_fmdemod((const float2*)in_dev, out_dev, count, h->phasor_speed, h->st.p + h->cur,
+                       h->st.p + (h->cur ^ 1), h->stereo, as_stream(s)) != 0)
+        return -1;
+    h->cur ^= 1;
+    return count;
+}
+
+}  // extern "C"
+
+// =================================================================================================
+// fused VFO -> FM demod, and the channelizer (N of them off one input)
+// =================================================================================================
+struct qdsp_channelizer {
+    int nch = 1;
+    float in_sr = 0, out_sr = 0, bw = 0, dev = 0;
+    int T = 0, interp = 1, decim = 1, tpp = 0;
+    float phasor_speed = 1.0f;
+    std::vector<float> taps;
+    std::vector<Nco> nco;        // per channel, host copy
+    NcoDev* nco_dev = nullptr;   // per channel constants
+    float* phases_dev = nullptr;
+    History hist;                // raw (untranslated) input tail, shared by all channels
+    Partition part;
+    DecimPlan* plan = nullptr;
+    DevState demod;              // [2][nch] ping-pong
+    int cur = 0;
+    long long abs_pos = 0;       // absolute index of the next input sample (NCO closed form)
+    int variant = 0;
+    // end-to-end staging (process_host)
+    void* stage_in[2] = {nullptr, nullptr};
+    float* stage_out[2] = {nullptr, nullptr};
+    cudaEvent_t ev_done[2] = {nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;
+    size_t stage_samples = 0;
+
+    int upload_nco() {
+        std::vector<NcoDev> v(nch);
+        for (int c = 0; c < nch; c++) v[c] = NcoDev{nco[c].phase, nco[c].step};
+        if (!nco_dev) QDSP_CUDA_OK(cudaMalloc(&nco_dev, sizeof(NcoDev) * nch));
+        QDSP_CUDA_OK(cudaDeviceSynchronize());
+        QDSP_CUDA_OK(cudaMemcpy(nco_dev, v.data(), sizeof(NcoDev) * nch, cudaMemcpyHostToDevice));
+        return 0;
+    }
+    int setup(int nch_, const float* offsets, float inSR, float outSR, float bandWidth, float deviation) {
+        nch = nch_;
+        in_sr = inSR;
+        out_sr = outSR;
+        bw = bandWidth;
+        dev = deviation;
+        T = qdsp_vfo_design(inSR, outSR, bandWidth, nullptr, 0, &interp, &decim);
+        taps.resize(T);
+        qdsp_vfo_design(inSR, outSR, bandWidth, taps.data(), T, &interp, &decim);
+        std::vector<float> ph = build_phases(taps.data(), T, interp, &tpp);
+        if (upload_floats(&phases_dev, ph) != 0) return -1;
+        if (hist.init(tpp, 8) != 0) return -1;
+        nco.resize(nch);
+        for (int c = 0; c < nch; c++) {
+            nco[c].set_freq(inSR, -offsets[c]);  // VFO::init: xlator.init(in, inSR, -offset), vfo.h:28
+            nco[c].phase = 0;
+        }
+        if (upload_nco() != 0) return -1;
+        phasor_speed = fm_phasor_speed(outSR, deviation);
+        std::vector<float> z(2 * nch, 0.0f);
+        if (demod.init(2 * nch, z.data()) != 0) return -1;
+        if (decim_plan_supported(T, interp, decim)) plan = decim_plan_create(taps.data(), T, decim);
+        return 0;
+    }
+    long long process(const void* in_dev, float* audio, void* iq, long long out_stride, long long count,
+                      const int* blocks, int nblocks, int block_size, int* out_counts, cudaStream_t s) {
+        if (part.build(count, blocks, nblocks, block_size, interp, decim, s) != 0) return -1;
+        if (out_counts) {
+            for (int b = 0; b < part.view.nblocks; b++) {
+                if (blocks) out_counts[b] = part.host[b].out_count;
+                else {
+                    const long long st = (long long)b * part.view.block_size;
+                    const long long c = count - st < part.view.block_size ? count - st : part.view.block_size;
+                    out_counts[b] = (int)((c * interp) / decim);
+                }
+            }
+        }
+        if (count == 0) return 0;
+        const float* din = demod.p + (size_t)cur * nch;
+        float* dout = demod.p + (size_t)(cur ^ 1) * nch;
+        int rc;
+        if (plan && variant != 1)
+            rc = launch_decim(plan, (const float2*)hist.ptr(), hist.H, (const float2*)in_dev, part, 1, nco_dev,
+                              abs_pos, nch, phasor_speed, din, dout, (float2*)iq, audio, out_stride, s);
+        else
+            rc = launch_generic_vfofm((const float2*)hist.ptr(), hist.H, (const float2*)in_dev, phases_dev, tpp, part,
+                                      nco_dev, abs_pos, nch, phasor_speed, din, dout, audio, (float2*)iq, out_stride,
+                                      s);
+        if (rc != 0) return -1;
+        if (part.total_out > 0) cur ^= 1;
+        if (hist.advance(in_dev, count, s) != 0) return -1;
+        abs_pos += count;
+        return part.total_out;
+    }
+    ~qdsp_channelizer() {
+        if (nco_dev) cudaFree(nco_dev);
+        if (phases_dev) cudaFree(phases_dev);
+        if (plan) decim_plan_destroy(plan);
+        hist.release();
+        for (int i = 0; i < 2; i++) {
+            if (stage_in[i]) cudaFree(stage_in[i]);
+            if (stage_out[i]) cudaFree(stage_out[i]);
+            if (ev_done[i]) cudaEventDestroy(ev_done[i]);
+        }
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+    }
+};
+struct qdsp_vfofm {
+    qdsp_channelizer c;
+};
+
+extern "C" {
+
+qdsp_vfofm* qdsp_vfofm_create(float offset, float inSampleRate, float outSampleRate, float bandWidth,
+                              float deviation) {
+    qdsp_vfofm* h = new (std::nothrow) qdsp_vfofm();
+    if (!h) return nullptr;
+    if (h->c.setup(1, &offset, inSampleRate, outSampleRate, bandWidth, deviation) != 0) {
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+void qdsp_vfofm_destroy(qdsp_vfofm* h) { delete h; }
+int qdsp_vfofm_design(qdsp_vfofm* h, int* tapCount, int* interp, int* decim) {
+    if (tapCount) *tapCount = h->c.T;
+    if (interp) *interp = h->c.interp;
+    if (decim) *decim = h->c.decim;
+    return 0;
+}
+int qdsp_vfofm_set_offset(qdsp_vfofm* h, float offset) {
+    // keep the phase continuous at the current position: phase(abs_pos) is preserved
+    Nco& n = h->c.nco[0];
+    const uint64_t cur_phase = n.phase + n.step * (uint64_t)h->c.abs_pos;
+    n.set_freq(h->c.in_sr, -offset);
+    n.phase = cur_phase - n.step * (uint64_t)h->c.abs_pos;
+    return h->c.upload_nco();
+}
+long long qdsp_vfofm_out_count(qdsp_vfofm* h, long long count, const int* blocks, int nblocks, int block_size) {
+    Partition p;
+    if (p.build(count, blocks, nblocks, block_size, h->c.interp, h->c.decim, nullptr) != 0) return -1;
+    return p.total_out;
+}
+long long qdsp_vfofm_process(qdsp_vfofm* h, const void* in_dev, float* audio_out_dev, void* iq_out_dev,
+                             long long count, const int* blocks, int nblocks, int block_size, int* out_counts,
+                             qdsp_stream_t s) {
+    return h->c.process(in_dev, audio_out_dev, iq_out_dev, 0, count, blocks, nblocks, block_size, out_counts,
+                        as_stream(s));
+}
+// Host-buffer entry point: the stream is cut into chunks of whole run()-blocks; chunk i+1's H2D copy
+// (copy stream) overlaps chunk i's kernel (compute stream) and chunk i-1's D2H.
+long long qdsp_vfofm_process_host(qdsp_vfofm* h, const void* in_host, float* audio_out_host, long long count,
+                                  int block_size, qdsp_stream_t s_) {
+    qdsp_channelizer& c = h->c;
+    cudaStream_t s = as_stream(s_);
+    if (block_size <= 0) block_size = 1000000;
+    const long long blocks_per_chunk = (8ll << 20) / block_size > 0 ? (8ll << 20) / block_size : 1;  // ~64 MiB of cf32
+    const size_t chunk = (size_t)(blocks_per_chunk * block_size);
+    if (c.stage_samples < chunk) {
+        for (int i = 0; i < 2; i++) {
+            if (c.stage_in[i]) cudaFree(c.stage_in[i]);
+            if (c.stage_out[i]) cudaFree(c.stage_out[i]);
+            c.stage_in[i] = nullptr;
+            c.stage_out[i] = nullptr;
+            QDSP_CUDA_OK(cudaMalloc(&c.stage_in[i], chunk * sizeof(float2)));
+            QDSP_CUDA_OK(cudaMalloc((void**)&c.stage_out[i], (chunk * c.interp / c.decim + 64) * sizeof(float)));
+            if (!c.ev_done[i]) QDSP_CUDA_OK(cudaEventCreateWithFlags(&c.ev_done[i], cudaEventDisableTiming));
+        }
+        if (!c.copy_stream) QDSP_CUDA_OK(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+        c.stage_samples = chunk;
+    }
+    cudaEvent_t ev_h2d[2];
+    for (int i = 0; i < 2; i++) QDSP_CUDA_OK(cudaEventCreateWithFlags(&ev_h2d[i], cudaEventDisableTiming));
+    const char* src = (const char*)in_host;
+    long long done = 0, produced = 0;
+    int slot = 0;
+    bool used[2] = {false, false};
+    while (done < count) {
+        const long long n = count - done < (long long)chunk ? count - done : (long long)chunk;
+        // the slot's previous kernel + D2H must have drained before its input buffer is overwritten
+        if (used[slot]) QDSP_CUDA_OK(cudaStreamWaitEvent(c.copy_stream, c.ev_done[slot], 0));
+        QDSP_CUDA_OK(cudaMemcpyAsync(c.stage_in[slot], src + (size_t)done * sizeof(float2), (size_t)n * sizeof(float2),
+                                     cudaMemcpyHostToDevice, c.copy_stream));
+        QDSP_CUDA_OK(cudaEventRecord(ev_h2d[slot], c.copy_stream));
+        QDSP_CUDA_OK(cudaStreamWaitEvent(s, ev_h2d[slot], 0));
+        const long long m = c.process(c.stage_in[slot], c.stage_out[slot], nullptr, 0, n, nullptr, 0, block_size, nullptr, s);
+        if (m < 0) return -1;
+        if (m > 0)
+            QDSP_CUDA_OK(cudaMemcpyAsync(audio_out_host + produced, c.stage_out[slot], (size_t)m * sizeof(float),
+                                         cudaMemcpyDeviceToHost, s));
+        QDSP_CUDA_OK(cudaEventRecord(c.ev_done[slot], s));
+        used[slot] = true;
+        produced += m;
+        done += n;
+        slot ^= 1;
+    }
+    QDSP_CUDA_OK(cudaStreamSynchronize(s));
+    for (int i = 0; i < 2; i++) cudaEventDestroy(ev_h2d[i]);
+    return produced;
+}
+int qdsp_vfofm_reset(qdsp_vfofm* h) {
+    qdsp_channelizer& c = h->c;
+    QDSP_CUDA_OK(cudaDeviceSynchronize());
+    if (c.hist.reset(nullptr) != 0) return -1;
+    std::vector<float> z(2 * c.nch, 0.0f);
+    if (c.demod.set(z.data(), 2 * c.nch) != 0) return -1;
+    c.abs_pos = 0;
+    c.cur = 0;
+    return 0;
+}
+int qdsp_vfofm_set_variant(qdsp_vfofm* h, int variant) {
+    h->c.variant = variant;
+    return 0;
+}
+int qdsp_vfofm_seek(qdsp_vfofm* h, long long start) {
+    h->c.abs_pos = start;
+    return 0;
+}
+int qdsp_vfofm_import_tail(qdsp_vfofm* h, const void* tail_dev, int src_device, qdsp_stream_t s) {
+    return import_tail_impl(h->c.hist, tail_dev, src_device, as_stream(s));
+}
+int qdsp_vfofm_history_len(qdsp_vfofm* h) { return h->c.hist.H; }
+
+qdsp_channelizer* qdsp_channelizer_create(int nch, const float* offsets, float inSampleRate, float outSampleRate,
+                                          float bandWidth, float deviation) {
+    if (nch <= 0 || !offsets) {
+        set_last_error("channelizer_create: bad arguments");
+        return nullptr;
+    }
+    qdsp_channelizer* h = new (std::nothrow) qdsp_channelizer();
+    if (!h) return nullptr;
+    if (h->setup(nch, offsets, inSampleRate, outSampleRate, bandWidth, deviation) != 0) {
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+void qdsp_channelizer_destroy(qdsp_channelizer* h) { delete h; }
+int qdsp_channelizer_design(qdsp_channelizer* h, int* tapCount, int* interp, int* decim) {
+    if (tapCount) *tapCount = h->T;
+    if (interp) *interp = h->interp;
+    if (decim) *decim = h->decim;
+    return 0;
+}
+long long qdsp_channelizer_process(qdsp_channelizer* h, const void* in_dev, float* audio_out_dev,
+                                   long long out_stride, long long count, const int* blocks, int nblocks,
+                                   int block_size, qdsp_stream_t s) {
+    return h->process(in_dev, audio_out_dev, nullptr, out_stride, count, blocks, nblocks, block_size, nullptr,
+                      as_stream(s));
+}
+int qdsp_channelizer_reset(qdsp_channelizer* h) {
+    QDSP_CUDA_OK(cudaDeviceSynchronize());
+    if (h->hist.reset(nullptr) != 0) return -1;
+    std::vector<float> z(2 * h->nch, 0.0f);
+    if (h->demod.set(z.data(), 2 * h->nch) != 0) return -1;
+    h->abs_pos = 0;
+    h->cur = 0;
+    return 0;
+}
+int qdsp_channelizer_set_variant(qdsp_channelizer* h, int variant) {
+    h->variant = variant;
+    return 0;
+}
+
+}  // extern "C"
+
+// =================================================================================================
+// recurrent blocks
+// =================================================================================================
+struct qdsp_deemp {
+    float alpha = 0.0f;
+    DevState st;  // [4]: in (l, r), out (l, r)
+};
+struct qdsp_agc {
+    float corrected = 0.0f;
+    DevState st;  // [1]: level
+    Partition part;
+    Scratch scratch;
+};
+struct qdsp_cagc {
+    float set_point = 1.0f, max_gain = 65535.0f, rate = 1e-3f;
+    DevState st;  // [1]: gain
+    Scratch scratch;
+};
+struct qdsp_ffagc {
+    int dtype = QDSP_CF32;
+    History hist;     // up to 1023 pending elements (right-aligned)
+    int pending = 0;  // how many of them are real
+};
+struct qdsp_costas {
+    int order = 4;
+    float alpha = 0.0f, beta = 0.0f;
+    int chunk = 16384, warmup = 4096;
+    DevState st;   // [4] state + [1] residual
+    Scratch scratch;
+};
+
+extern "C" {
+
+qdsp_deemp* qdsp_deemp_create(float sampleRate, float tau) {
+    qdsp_deemp* h = new (std::nothrow) qdsp_deemp();
+    if (!h) return nullptr;
+    const float dt = 1.0f / sampleRate;  // filter.h:102-103
+    h->alpha = dt / (tau + dt);
+    const float z[4] = {0, 0, 0, 0};
+    if (h->st.init(4, z) != 0) {
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+void qdsp_deemp_destroy(qdsp_deemp* h) { delete h; }
+long long qdsp_deemp_process(qdsp_deemp* h, const void* in_dev, void* out_dev, long long count, qdsp_stream_t s) {
+    if (count < 0) return -1;
+    if (launch_deemp((const float2*)in_dev, (float2*)out_dev, count, h->alpha, h->st.p, nullptr, 0, as_stream(s)) != 0)
+        return -1;
+    return count;
+}
+int qdsp_deemp_get_state(qdsp_deemp* h, float* lastL, float* lastR) {
+    float v[2];
+    if (h->st.get(v, 2) != 0) return -1;
+    *lastL = v[0];
+    *lastR = v[1];
+    return 0;
+}
+int qdsp_deemp_set_state(qdsp_deemp* h, float lastL, float lastR) {
+    const float v[2] = {lastL, lastR};
+    return h->st.set(v, 2);
+}
+
+qdsp_agc* qdsp_agc_create(float fallRate, float sampleRate) {
+    qdsp_agc* h = new (std::nothrow) qdsp_agc();
+    if (!h) return nullptr;
+    h->corrected = fallRate / sampleRate;  // processing.h:92
+    const float z = 0.0f;                  // level = 0, processing.h:140
+    if (h->st.init(1, &z) != 0) {
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+void qdsp_agc_destroy(qdsp_agc* h) { delete h; }
+long long qdsp_agc_process(qdsp_agc* h, const float* in_dev, float* out_dev, long long count, const int* blocks,
+                           int nblocks, int block_size, qdsp_stream_t s_) {
+    cudaStream_t s = as_stream(s_);
+    if (h->part.build(count, blocks, nblocks, block_size, 1, 1, s) != 0) return -1;
+    const int nb = h->part.view.nblocks;
+    if (nb == 0) return 0;
+    if (h->scratch.reserve(sizeof(float) * 2 * (size_t)nb + 64) != 0) return -1;
+    float* bm = (float*)h->scratch.p;
+    if (launch_agc(in_dev, out_dev, h->part, h->corrected, h->st.p, bm, bm + nb, s) != 0) return -1;
+    return count;
+}
+int qdsp_agc_get_state(qdsp_agc* h, float* level) { return h->st.get(level, 1); }
+int qdsp_agc_set_state(qdsp_agc* h, float level) { return h->st.set(&level, 1); }
+
+qdsp_cagc* qdsp_cagc_create(float setPoint, float maxGain, float rate) {
+    qdsp_cagc* h = new (std::nothrow) qdsp_cagc();
+    if (!h) return nullptr;
+    h->set_point = setPoint;
+    h->max_gain = maxGain;
+    h->rate = rate;
+    const float one = 1.0f;  // _gain = 1, processing.h:291
+    if (h->st.init(1, &one) != 0) {
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+void qdsp_cagc_destroy(qdsp_cagc* h) { delete h; }
+long long qdsp_cagc_process(qdsp_cagc* h, const void* in_dev, void* out_dev, long long count, qdsp_stream_t s) {
+    if (count < 0) return -1;
+    if (count == 0) return 0;
+    if (h->scratch.reserve(scan_scratch_bytes(count)) != 0) return -1;
+    if (launch_cagc((const float2*)in_dev, (float2*)out_dev, count, h->set_point, h->max_gain, h->rate, h->st.p,
+                    h->scratch.p, h->scratch.cap, as_stream(s)) != 0)
+        return -1;
+    return count;
+}
+int qdsp_cagc_get_state(qdsp_cagc* h, float* gain) { return h->st.get(gain, 1); }
+int qdsp_cagc_set_state(qdsp_cagc* h, float gain) { return h->st.set(&gain, 1); }
+
+qdsp_ffagc* qdsp_ffagc_create(int dtype) {
+    qdsp_ffagc* h = new (std::nothrow) qdsp_ffagc();
+    if (!h) return nullptr;
+    h->dtype = dtype;
+    if (h->hist.init(1023, dtype == QDSP_CF32 ? 8 : 4) != 0) {
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+void qdsp_ffagc_destroy(qdsp_ffagc* h) {
+    if (!h) return;
+    h->hist.release();
+    delete h;
+}
+long long qdsp_ffagc_process(qdsp_ffagc* h, const void* in_dev, void* out_dev, long long count, qdsp_stream_t s_) {
+    cudaStream_t s = as_stream(s_);
+    if (count < 0) return -1;
+    if (count == 0) return 0;
+    // virtual stream = pending ++ in; outputs while a full 1024-window exists (processing.h:189-193)
+    const long long avail = h->pending + count;
+    const long long n_valid = avail >= 1024 ? avail - 1023 : 0;
+    if (n_valid > 0) {
+        // the kernel addresses the pending samples as virtual indices -pending..-1 (right-aligned tail)
+        const char* hp = (const char*)h->hist.ptr() + (size_t)(h->hist.H - h->pending) * h->hist.elem;
+        if (launch_ffagc(hp, h->pending, in_dev, out_dev, n_valid, h->dtype == QDSP_CF32, s) != 0) return -1;
+    }
+    if (h->hist.advance(in_dev, count, s) != 0) return -1;
+    h->pending = (int)(avail - n_valid < 1023 ? avail - n_valid : 1023);
+    return n_valid;
+}
+
+qdsp_costas* qdsp_costas_create(int order, float loopBandwidth) {
+    if (order != 2 && order != 4 && order != 8) {
+        set_last_error("costas_create: order must be 2, 4 or 8");
+        return nullptr;
+    }
+    qdsp_costas* h = new (std::nothrow) qdsp_costas();
+    if (!h) return nullptr;
+    h->order = order;
+    // pll.h:20-23 (float/double mix as written there)
+    const float damp = sqrtf(2.0f) / 2.0f;
+    const float den = (float)(1.0 + 2.0 * damp * loopBandwidth + loopBandwidth * loopBandwidth);
+    h->alpha = (4 * damp * loopBandwidth) / den;
+    h->beta = (4 * loopBandwidth * loopBandwidth) / den;
+    const float init[5] = {0.0f, 0.0f, 1.0f, 0.0f, 0.0f};
+    if (h->st.init(5, init) != 0) {
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+void qdsp_costas_destroy(qdsp_costas* h) { delete h; }
+long long qdsp_costas_process(qdsp_costas* h, const void* in_dev, void* out_dev, long long count, qdsp_stream_t s) {
+    if (count < 0) return -1;
+    if (count == 0) return 0;
+    if (h->scratch.reserve(costas_scratch_bytes(count, h->chunk)) != 0) return -1;
+    if (launch_costas((const float2*)in_dev, (float2*)out_dev, count, h->order, h->alpha, h->beta, h->st.p, h->chunk,
+                      h->warmup, h->scratch.p, h->scratch.cap, h->st.p + 4, as_stream(s)) != 0)
+        return -1;
+    return count;
+}
+int qdsp_costas_get_state(qdsp_costas* h, float state[4]) { return h->st.get(state, 4); }
+int qdsp_costas_set_state(qdsp_costas* h, const float state[4]) { return h->st.set(state, 4); }
+int qdsp_costas_set_chunking(qdsp_costas* h, int chunk, int warmup) {
+    h->chunk = chunk;
+    h->warmup = warmup;
+    return 0;
+}
+float qdsp_costas_last_residual(qdsp_costas* h) {
+    float r = -1.0f;
+    h->st.get(&r, 1, 4);
+    return r;
+}
+
+// =================================================================================================
+// synthetic IQ + probes
+// =================================================================================================
+int qdsp_synth_uniform_cf32(void* out_dev, unsigned long long seed, long long start, long long count,
+                            qdsp_stream_t s) {
+    return launch_synth_uniform((float2*)out_dev, seed, start, count, as_stream(s));
+}
+int qdsp_synth_fm_cf32(void* out_dev, long long start, long long count, long long fs, long long fc, long long fm,
+                       double dev, double amp, double noise_amp, unsigned long long noise_seed, qdsp_stream_t s) {
+    return launch_synth_fm((float2*)out_dev, start, count, fs, fc, fm, dev, amp, noise_amp, noise_seed, as_stream(s));
+}
+double qdsp_measure_fp32_peak(int packed, int iters) { return run_fp32_peak(packed, iters); }
+
+}  // extern "C"

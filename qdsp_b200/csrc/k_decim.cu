@@ -1,0 +1,449 @@
+// qdsp_b200/csrc/k_decim.cu — column-parallel decimating FIR for sm_100a (interp = 1, even decim D),
+// with an optional NCO prologue and FM-demod epilogue: the fused xlate -> resample -> demod pass of
+// the reference's VFO + FloatFMDemod chain (vfo.h:19-36, resampling.h:99-132, demodulator.h:81-99).
+//
+// Formulation. View the stream as a matrix with rows of D samples. With taps zero-padded to Q*D,
+//     y[k] = sum_{r<D} sum_{q<Q} g[q*D + r] * x'[base + (k+q)*D + r]
+// so column r is a Q-tap FIR over the column's own sub-stream. A thread owns a PAIR of adjacent
+// columns and keeps their Q tap pairs in registers; it walks down the rows with Q partial outputs in
+// flight (static register rotation: the row loop is unrolled by Q). One FFMA2 (packed f32x2) does
+// the two columns' MACs for re, another for im: (re[r], re[r+1]) * (g[r], g[r+1]) — no duplicated
+// tap registers, one 128-bit shared-memory load per 2 samples per 2*Q FFMA2.
+//
+// Data movement. A CTA covers NSEG row segments of L outputs each; every segment streams its rows
+// through a ring of NSTAGE shared-memory stages filled by TMA bulk copies (cp.async.bulk, completion
+// on an mbarrier) — R rows per stage per segment. Segments whose chunk would cross the ends of the
+// caller's buffer (history before sample 0, ragged tail) are filled by guarded loads instead.
+// Column partial sums are exchanged through a small double-buffered shared array and reduced by
+// 8-lane groups; the epilogue applies fast_arctan2 + phase difference on chip, so neither the
+// translated nor the resampled IQ ever reaches HBM (unless the caller asks for the IQ).
+#include <new>
+#include <vector>
+#include "internal.cuh"
+#include "kernels.cuh"
+
+namespace qdsp {
+
+struct DecimPlan {
+    int T = 0, D = 0, Q = 0, P = 0;
+    int NSEG = 0, R = 0, NSTAGE = 0, NSUP = 0, NT = 0;
+    float2* taps_dev = nullptr;  // [2][Q][P] tap pairs for pad = 0 / 1 (g[t] = h[t - pad])
+};
+
+struct DecimArgs {
+    const float2* hist;
+    const float2* in;
+    int H;
+    long long n_in;
+    const float2* taps;  // [2][Q][P]
+    PartitionDev part;
+    int T, D, P, NSEG, R, NSTAGE, NSUP, L;
+    const NcoDev* nco;
+    long long abs0;
+    float phasor_speed;
+    const float* demod_in;
+    float* demod_out;
+    float2* out_iq;
+    float* audio;
+    long long out_stride;
+};
+
+// ---- PTX wrappers: mbarrier + TMA bulk copy (SASS: SYNCS / UBLKCP) -----------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// single output by brute force (warp-cooperative): used for the one "previous output" a block's first
+// tile needs when the previous run() block did not end on the decimation grid.
+template <bool ROT>
+__device__ float2 direct_output_warp(const DecimArgs& a, long long win_start, uint64_t ph0, uint64_t step) {
+    // y = sum_t h[t] * x'[win_start + t]; taps table pad=0 holds h at [q][p] pairs == flat h[t]
+    const float* h = reinterpret_cast<const float*>(a.taps);
+    const int lane = threadIdx.x & 31;
+    VStream<float2> xs{a.hist, a.in, a.H};
+    float2 acc = make_float2(0.f, 0.f);
+    for (int t = lane; t < a.T; t += 32) {
+        const long long i = win_start + t;
+        float2 v = (i < a.n_in) ? xs.at(i) : make_float2(0.f, 0.f);
+        if (ROT) v = cmul(v, phasor_from_turns(ph0 + step * (uint64_t)i));
+        acc.x = fmaf(v.x, h[t], acc.x);
+        acc.y = fmaf(v.y, h[t], acc.y);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+    }
+    return acc;
+}
+
+template <int Q, int R, bool ROT, bool DEMOD, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
+    constexpr int LEAD = DEMOD ? 1 : 0;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int D = a.D, P = a.P, NSEG = a.NSEG, NSTAGE = a.NSTAGE, L = a.L;
+    const int NT = blockDim.x;
+    const int t = threadIdx.x;
+    const int b = blockIdx.y, ch = blockIdx.z;
+    const BlkInfo bi = a.part.get(b);
+    const int k0 = blockIdx.x * (NSEG * L);
+    if (k0 >= bi.out_count) return;
+
+    // ---- shared memory carve-up --------------------------------------------------------------
+    const int chunk_elems = R * D;                        // per segment per stage
+    const size_t stage_bytes = (size_t)NSEG * chunk_elems * sizeof(float2);
+    const int Ppad = P | 1;
+    float2* X = reinterpret_cast<float2*>(smem_raw);
+    float2* Pbuf = reinterpret_cast<float2*>(smem_raw + (size_t)NSTAGE * stage_bytes);  // [2][NSEG*R][Ppad]
+    float* s_ang = reinterpret_cast<float*>(Pbuf + 2 * NSEG * R * Ppad);                  // [NSEG][L+LEAD]
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(
+        (reinterpret_cast<uintptr_t>(s_ang + NSEG * (L + LEAD)) + 15) & ~(uintptr_t)15);   // [NSTAGE]
+    float* s_misc = reinterpret_cast<float*>(mbar + NSTAGE);                              // [0]=override angle
+
+    // ---- thread roles ------------------------------------------------------------------------
+    const int seg = t / P;
+    const int pair = t - seg * P;
+    const bool in_grid = seg < NSEG;
+    const int pad = (int)((bi.in_start - a.T) & 1);
+    const int ks = k0 + seg * L - LEAD;  // first output (the leading one when DEMOD) of this segment
+    const long long seg_base = bi.in_start + (long long)ks * D - a.T - pad;
+    const bool seg_active = in_grid && (k0 + seg * L < bi.out_count);
+    // rows this CTA really needs: its fullest segment (segment 0) has min(L, out_count - k0) outputs
+    const int need = (bi.out_count - k0 < L ? bi.out_count - k0 : L) + LEAD + Q - 1;
+    const int nsup = (need + Q - 1) / Q < a.NSUP ? (need + Q - 1) / Q : a.NSUP;
+    const int nst = nsup * (Q / R);
+
+    uint64_t nco_step = 0, nco_ph0 = 0;
+    if (ROT) {
+        nco_step = a.nco[ch].step;
+        nco_ph0 = a.nco[ch].init + nco_step * (uint64_t)a.abs0;
+    }
+
+    if (t == 0) {
+        for (int s = 0; s < NSTAGE; s++) mbar_init(&mbar[s], NSEG);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // leading-angle override of the block's very first output (warp 0)
+    bool use_override = false;
+    if (DEMOD && blockIdx.x == 0) {
+        int pb = b - 1;
+        BlkInfo pbi{};
+        while (pb >= 0) {
+            pbi = a.part.get(pb);
+            if (pbi.out_count > 0) break;
+            pb--;
+        }
+        if (pb < 0) {
+            use_override = true;
+            if (t == 0) s_misc[0] = a.demod_in[ch];
+        } else if (pb != b - 1 || pbi.in_start + (long long)pbi.out_count * D != bi.in_start) {
+            use_override = true;  // previous block's last output is off this block's row grid
+            if (t < 32) {
+                const float2 y = direct_output_warp<ROT>(
+                    a, pbi.in_start + (long long)(pbi.out_count - 1) * D - a.T, nco_ph0, nco_step);
+                if (t == 0) s_misc[0] = fast_arctan2_ref(y.y, y.x);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- producer: one TMA bulk copy per (segment, stage); guarded fill at the buffer ends ---------
+    auto issue = [&](int it) {
+        if (!in_grid) return;
+        const int slot = it % NSTAGE;
+        const long long start = seg_base + (long long)it * chunk_elems;
+        float2* dst = X + (size_t)slot * NSEG * chunk_elems + (size_t)seg * chunk_elems;
+        const bool live = seg_active && it < nst;
+        const bool fast = live && start >= 0 && start + chunk_elems <= a.n_in;
+        if (pair == 0) {
+            if (fast) {
+                mbar_arrive_expect_tx(&mbar[slot], (uint32_t)(chunk_elems * sizeof(float2)));
+                tma_bulk_g2s(dst, a.in + start, (uint32_t)(chunk_elems * sizeof(float2)), &mbar[slot]);
+            } else {
+                mbar_arrive(&mbar[slot]);
+            }
+        }
+        if (live && !fast) {
+            VStream<float2> xs{a.hist, a.in, a.H};
+            for (int e = pair; e < chunk_elems; e += P) {
+                const long long i = start + e;
+                dst[e] = (i < a.n_in) ? xs.at(i) : make_float2(0.f, 0.f);
+            }
+        }
+    };
+
+    // ---- per-thread constants: tap pairs, phasors -------------------------------------------------
+    float2 tp[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) tp[q] = make_float2(0.f, 0.f);
+    if (in_grid) {
+        const float2* tt = a.taps + (size_t)pad * Q * P;
+#pragma unroll
+        for (int q = 0; q < Q; q++) tp[q] = tt[q * P + pair];
+    }
+    float2 p0 = make_float2(1.f, 0.f), p1 = make_float2(1.f, 0.f), w = make_float2(1.f, 0.f);
+    const long long col0 = seg_base + 2 * pair;  // sample index of (row 0, first column of the pair)
+    if (ROT) w = phasor_from_turns(nco_step * (uint64_t)D);
+
+    float2 accRe[Q], accIm[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) accRe[q] = accIm[q] = make_float2(0.f, 0.f);
+
+    for (int it = 0; it < NSTAGE; it++) issue(it);
+    __syncthreads();
+
+    // ---- reduction of one stage's column partials + epilogue ----------------------------------------
+    auto reduce_stage = [&](int it) {
+        const float2* pb = Pbuf + (size_t)(it & 1) * NSEG * R * Ppad;
+        const int u = t & 7;
+        // warp-uniform trip count: every lane runs the shuffles, out-of-range groups just add zeros
+        for (int ob = (t >> 5) * 4; ob < NSEG * R; ob += (NT >> 5) * 4) {
+            const int o = ob + ((t & 31) >> 3);
+            const bool ovalid = o < NSEG * R;
+            float2 s = make_float2(0.f, 0.f);
+            if (ovalid) {
+                for (int pp = u; pp < P; pp += 8) {
+                    const float2 v = pb[o * Ppad + pp];
+                    s.x += v.x;
+                    s.y += v.y;
+                }
+            }
+#pragma unroll
+            for (int sh = 4; sh > 0; sh >>= 1) {
+                s.x += __shfl_xor_sync(0xffffffffu, s.x, sh);
+                s.y += __shfl_xor_sync(0xffffffffu, s.y, sh);
+            }
+            if (u == 0 && ovalid) {
+                const int so = o / R, ro = o - so * R;
+                const int j = it * R + ro - (Q - 1);  // output index within the segment (0 = leading)
+                const int k = k0 + so * L - LEAD + j;
+                if (j >= 0 && j < L + LEAD && k < bi.out_count && k0 + so * L < bi.out_count) {
+                    if (DEMOD) {
+                        float ang = fast_arctan2_ref(s.y, s.x);
+                        if (use_override && so == 0 && j == 0) ang = s_misc[0];
+                        s_ang[so * (L + LEAD) + j] = ang;
+                        if (a.out_iq && j >= LEAD) a.out_iq[ch * a.out_stride + bi.out_start + k] = s;
+                    } else {
+                        a.out_iq[ch * a.out_stride + bi.out_start + k] = s;
+                    }
+                }
+            }
+        }
+    };
+    auto demod_stage = [&](int it) {
+        if (!DEMOD) return;
+        for (int o = t; o < NSEG * R; o += NT) {
+            const int so = o / R, ro = o - so * R;
+            const int j = it * R + ro - (Q - 1);
+            const int k = k0 + so * L - LEAD + j;
+            if (j >= LEAD && j < L + LEAD && k < bi.out_count) {
+                const float cur = s_ang[so * (L + LEAD) + j], prev = s_ang[so * (L + LEAD) + j - 1];
+                a.audio[ch * a.out_stride + bi.out_start + k] = fm_step_ref(cur, prev, a.phasor_speed);
+                if (bi.out_start + k == a.part.total_out - 1) a.demod_out[ch] = cur;
+            }
+        }
+    };
+
+    // ---- main loop: NSUP super-iterations of Q rows (= Q/R stages) ----------------------------------
+    const int rowstride4 = D / 2;  // float4 per row
+#pragma unroll 1
+    for (int sup = 0; sup < nsup; sup++) {
+        if (ROT && (sup & 3) == 0 && seg_active) {
+            // exact phasor re-seed (closed form) every 4*Q rows bounds the recurrence's rounding walk
+            const long long i0 = col0 + (long long)sup * Q * D;
+            p0 = phasor_from_turns(nco_ph0 + nco_step * (uint64_t)i0);
+            p1 = phasor_from_turns(nco_ph0 + nco_step * (uint64_t)(i0 + 1));
+        }
+#pragma unroll
+        for (int i = 0; i < Q; i++) {
+            const int it = sup * (Q / R) + i / R;
+            const int slot = it % NSTAGE;
+            if (i % R == 0) mbar_wait(&mbar[slot], (uint32_t)((it / NSTAGE) & 1));
+            if (seg_active) {
+                const float4* xr = reinterpret_cast<const float4*>(X + (size_t)slot * NSEG * chunk_elems +
+                                                                   (size_t)seg * chunk_elems) +
+                                   (i % R) * rowstride4 + pair;
+                const float4 v = *xr;
+                float2 x0 = make_float2(v.x, v.y), x1 = make_float2(v.z, v.w);
+                if (ROT) {
+                    x0 = cmul(x0, p0);
+                    x1 = cmul(x1, p1);
+                    p0 = cmul(p0, w);
+                    p1 = cmul(p1, w);
+                }
+                const float2 RE = make_float2(x0.x, x1.x), IM = make_float2(x0.y, x1.y);
+#pragma unroll
+                for (int q = 0; q < Q; q++) {
+                    const int sl = (i - q + Q) % Q;
+                    if (q == 0) {
+                        accRe[sl] = __fmul2_rn(RE, tp[0]);
+                        accIm[sl] = __fmul2_rn(IM, tp[0]);
+                    } else {
+                        accRe[sl] = __ffma2_rn(RE, tp[q], accRe[sl]);
+                        accIm[sl] = __ffma2_rn(IM, tp[q], accIm[sl]);
+                    }
+                }
+                const int e = (i + 1) % Q;  // the output whose last tap (q = Q-1) was just applied
+                Pbuf[(size_t)(it & 1) * NSEG * R * Ppad + (seg * R + (i % R)) * Ppad + pair] =
+                    make_float2(accRe[e].x + accRe[e].y, accIm[e].x + accIm[e].y);
+            }
+            if (i % R == R - 1) {
+                __syncthreads();            // stage consumed, partials visible
+                issue(it + NSTAGE);         // refill the slot just drained
+                reduce_stage(it);
+                if (it > 0) demod_stage(it - 1);
+            }
+        }
+    }
+    __syncthreads();
+    demod_stage(nst - 1);
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+bool decim_plan_supported(int T, int interp, int decim) {
+    if (interp != 1 || (decim & 1) || decim < 8) return false;
+    const int Q = (T + 1 + decim - 1) / decim;
+    if (Q > 9 || Q < 2) return false;       // instantiated: Q in {3, 6, 9} (padded up)
+    if (decim / 2 > 640) return false;
+    return true;
+}
+static int round_q(int Q) { return Q <= 3 ? 3 : Q <= 6 ? 6 : 9; }
+
+DecimPlan* decim_plan_create(const float* taps, int T, int D) {
+    if (!decim_plan_supported(T, 1, D)) return nullptr;
+    DecimPlan* p = new (std::nothrow) DecimPlan();
+    if (!p) return nullptr;
+    p->T = T;
+    p->D = D;
+    p->P = D / 2;
+    p->Q = round_q((T + 1 + D - 1) / D);
+    p->R = 3;
+    p->NSTAGE = 4;
+    // segments per CTA: fill ~416 threads
+    int nseg = 416 / p->P;
+    if (nseg < 1) nseg = 1;
+    if (nseg > 32) nseg = 32;
+    p->NSEG = nseg;
+    p->NT = ((nseg * p->P + 31) / 32) * 32;
+    if (p->NT < 64) p->NT = 64;
+    p->NSUP = 15;
+    std::vector<float2> tab((size_t)2 * p->Q * p->P, make_float2(0.f, 0.f));
+    for (int pad = 0; pad < 2; pad++)
+        for (int q = 0; q < p->Q; q++)
+            for (int c = 0; c < p->P; c++) {
+                const int t0 = q * D + 2 * c - pad, t1 = t0 + 1;
+                float2 v;
+                v.x = (t0 >= 0 && t0 < T) ? taps[t0] : 0.0f;
+                v.y = (t1 >= 0 && t1 < T) ? taps[t1] : 0.0f;
+                tab[((size_t)pad * p->Q + q) * p->P + c] = v;
+            }
+    if (cudaMalloc(&p->taps_dev, tab.size() * sizeof(float2)) != cudaSuccess ||
+        cudaMemcpy(p->taps_dev, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_last_error("decim_plan_create: tap upload failed");
+        delete p;
+        return nullptr;
+    }
+    return p;
+}
+void decim_plan_destroy(DecimPlan* p) {
+    if (!p) return;
+    if (p->taps_dev) cudaFree(p->taps_dev);
+    delete p;
+}
+
+template <int Q, bool ROT, bool DEMOD>
+static int launch_decim_t(const DecimArgs& a, dim3 grid, int NT, size_t smem, cudaStream_t s) {
+    if (NT <= 448) {
+        auto kern = decim_kernel<Q, 3, ROT, DEMOD, 448, 2>;
+        QDSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, NT, smem, s>>>(a);
+    } else {
+        auto kern = decim_kernel<Q, 3, ROT, DEMOD, 640, 1>;
+        QDSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, NT, smem, s>>>(a);
+    }
+    QDSP_LAUNCH_OK();
+    return 0;
+}
+
+int launch_decim(DecimPlan* plan, const float2* hist, int H, const float2* in, const Partition& part, int mode,
+                 const NcoDev* nco, long long abs0, int nch, float phasor_speed, const float* demod_in,
+                 float* demod_out, float2* out_iq, float* audio, long long out_stride, cudaStream_t s) {
+    if (part.view.nblocks == 0 || part.max_out == 0) return 0;
+    if ((reinterpret_cast<uintptr_t>(in) & 15) != 0) {
+        set_last_error("decim: input pointer must be 16-byte aligned for TMA bulk copies");
+        return -1;
+    }
+    const int lead = mode == 1 ? 1 : 0;
+    DecimArgs a{};
+    a.hist = hist;
+    a.in = in;
+    a.H = H;
+    a.n_in = part.view.total;
+    a.taps = plan->taps_dev;
+    a.part = part.view;
+    a.T = plan->T;
+    a.D = plan->D;
+    a.P = plan->P;
+    a.NSEG = plan->NSEG;
+    a.R = plan->R;
+    a.NSTAGE = plan->NSTAGE;
+    a.NSUP = plan->NSUP;
+    a.L = plan->NSUP * plan->Q - (plan->Q - 1) - lead;
+    a.nco = nco;
+    a.abs0 = abs0;
+    a.phasor_speed = phasor_speed;
+    a.demod_in = demod_in;
+    a.demod_out = demod_out;
+    a.out_iq = out_iq;
+    a.audio = audio;
+    a.out_stride = out_stride;
+    const int per_tile = a.NSEG * a.L;
+    dim3 grid((part.max_out + per_tile - 1) / per_tile, part.view.nblocks, nch);
+    const size_t stage_bytes = (size_t)a.NSEG * a.R * a.D * sizeof(float2);
+    const size_t smem = (size_t)a.NSTAGE * stage_bytes + (size_t)2 * a.NSEG * a.R * (a.P | 1) * sizeof(float2) +
+                        (size_t)a.NSEG * (a.L + lead) * sizeof(float) + 16 + a.NSTAGE * 8 + 64;
+    if (smem > 227 * 1024) {
+        set_last_error("decim: tile does not fit shared memory (%zu bytes)", smem);
+        return -1;
+    }
+#define QDSP_DECIM_CASE(QQ)                                                                                   \
+    case QQ:                                                                                                  \
+        return mode == 1 ? launch_decim_t<QQ, true, true>(a, grid, plan->NT, smem, s)                         \
+                         : launch_decim_t<QQ, false, false>(a, grid, plan->NT, smem, s);
+    switch (plan->Q) {
+        QDSP_DECIM_CASE(3)
+        QDSP_DECIM_CASE(6)
+        QDSP_DECIM_CASE(9)
+    }
+#undef QDSP_DECIM_CASE
+    set_last_error("decim: unsupported Q=%d", plan->Q);
+    return -1;
+}
+
+}  // namespace qdsp

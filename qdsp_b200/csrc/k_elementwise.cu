@@ -1,0 +1,224 @@
+// qdsp_b200/csrc/k_elementwise.cu — streaming element-wise kernels: NCO frequency translator,
+// FM quadrature demodulator, pair-average decimator, device-side synthetic IQ, FP32-peak probe.
+// All are HBM-bound: 128-bit accesses, grid-stride over a grid sized in multiples of the SM count.
+#include "internal.cuh"
+#include "kernels.cuh"
+
+namespace qdsp {
+
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+static int stream_grid(long long work_items, int threads, int ctas_per_sm) {
+    long long g = (work_items + threads - 1) / threads;
+    const long long cap = (long long)sm_count() * ctas_per_sm;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+// ---- FrequencyXlator: out[n] = in[n] * phase(n)  (reference processing.h:64 + VOLK rotator) -----
+// phase(n) is the closed form of the reference's recursive float phasor (same float32 increment,
+// no drift, unit magnitude). Each thread rotates 4 consecutive samples: one exact phasor from the
+// 64-bit turn counter, three more from the host-rounded powers inc^1..inc^3.
+__global__ void __launch_bounds__(256) xlator_kernel(const float2* __restrict__ in, float2* __restrict__ out,
+                                                    long long count, uint64_t phase0, uint64_t step, float2 inc1,
+                                                    float2 inc2, float2 inc3) {
+    const long long nquad = count >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < nquad; q += stride) {
+        const long long n = q << 2;
+        const float4 a = ldg_stream128(reinterpret_cast<const float4*>(in + n));
+        const float4 b = ldg_stream128(reinterpret_cast<const float4*>(in + n + 2));
+        const float2 p0 = phasor_from_turns(phase0 + step * (uint64_t)n);
+        const float2 p1 = cmul(p0, inc1), p2 = cmul(p0, inc2), p3 = cmul(p0, inc3);
+        const float2 y0 = cmul_exact(make_float2(a.x, a.y), p0);
+        const float2 y1 = cmul_exact(make_float2(a.z, a.w), p1);
+        const float2 y2 = cmul_exact(make_float2(b.x, b.y), p2);
+        const float2 y3 = cmul_exact(make_float2(b.z, b.w), p3);
+        reinterpret_cast<float4*>(out + n)[0] = make_float4(y0.x, y0.y, y1.x, y1.y);
+        reinterpret_cast<float4*>(out + n)[1] = make_float4(y2.x, y2.y, y3.x, y3.y);
+    }
+    // ragged tail (count % 4) — one thread
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (long long n = nquad << 2; n < count; n++)
+            out[n] = cmul_exact(in[n], phasor_from_turns(phase0 + step * (uint64_t)n));
+    }
+}
+int launch_xlator(const float2* in, float2* out, long long count, uint64_t phase0, uint64_t step, float2 inc1,
+                  float2 inc2, float2 inc3, cudaStream_t s) {
+    if (count <= 0) return 0;
+    xlator_kernel<<<stream_grid(count / 4 + 1, 256, 8), 256, 0, s>>>(in, out, count, phase0, step, inc1, inc2, inc3);
+    QDSP_LAUNCH_OK();
+    return 0;
+}
+
+// ---- FloatFMDemod / FMDemod (reference demodulator.h:87-94 / 164-173) -------------------------------
+// out[i] = wrap(fast_arctan2(x[i]) - fast_arctan2(x[i-1])) / phasorSpeed; x[-1]'s angle is the carried
+// state. Each thread recomputes the neighbour's angle instead of exchanging it.
+__global__ void __launch_bounds__(256) fmdemod_kernel(const float2* __restrict__ in, void* __restrict__ out,
+                                                     long long count, float phasor_speed,
+                                                     const float* __restrict__ state_in,
+                                                     float* __restrict__ state_out, int stereo) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += stride) {
+        const float2 x = in[i];
+        const float cur = fast_arctan2_ref(x.y, x.x);
+        float prev;
+        if (i > 0) {
+            const float2 xp = in[i - 1];
+            prev = fast_arctan2_ref(xp.y, xp.x);
+        } else {
+            prev = *state_in;
+        }
+        const float v = fm_step_ref(cur, prev, phasor_speed);
+        if (stereo) reinterpret_cast<float2*>(out)[i] = make_float2(v, v);
+        else reinterpret_cast<float*>(out)[i] = v;
+        if (i == count - 1) *state_out = cur;
+    }
+}
+int launch_fmdemod(const float2* in, void* out, long long count, float phasor_speed, const float* state_in,
+                   float* state_out, int stereo, cudaStream_t s) {
+    if (count <= 0) return 0;
+    fmdemod_kernel<<<stream_grid(count, 256, 8), 256, 0, s>>>(in, out, count, phasor_speed, state_in, state_out,
+                                                              stereo);
+    QDSP_LAUNCH_OK();
+    return 0;
+}
+
+// ---- PowerDecimator (reference resampling.h:220-249) -----------------------------------------------
+__global__ void __launch_bounds__(256) power_decim_kernel(const float4* __restrict__ in, float2* __restrict__ out,
+                                                         long long n_out) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < n_out; m += stride) {
+        const float4 v = ldg_stream128(in + m);
+        out[m] = make_float2(__fmul_rn(__fadd_rn(v.x, v.z), 0.5f), __fmul_rn(__fadd_rn(v.y, v.w), 0.5f));
+    }
+}
+int launch_power_decim(const float2* in, float2* out, long long n_out, int copy_only, cudaStream_t s) {
+    if (n_out <= 0) return 0;
+    if (copy_only) {
+        QDSP_CUDA_OK(cudaMemcpyAsync(out, in, (size_t)n_out * sizeof(float2), cudaMemcpyDeviceToDevice, s));
+        return 0;
+    }
+    power_decim_kernel<<<stream_grid(n_out, 256, 8), 256, 0, s>>>(reinterpret_cast<const float4*>(in), out, n_out);
+    QDSP_LAUNCH_OK();
+    return 0;
+}
+
+// ---- synthetic IQ (integer recipe identical to qdsp_b200/synth.py) -------------------
+__device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ float2 uniform_sample(unsigned long long seed, long long n) {
+    const uint64_t z = splitmix64(((uint64_t)seed << 40) ^ (uint64_t)n);
+    const float re = (float)(uint32_t)(z & 0xFFFFFF) * 1.1920928955078125e-07f - 1.0f;
+    const float im = (float)(uint32_t)((z >> 24) & 0xFFFFFF) * 1.1920928955078125e-07f - 1.0f;
+    return make_float2(re, im);
+}
+__global__ void __launch_bounds__(256) synth_uniform_kernel(float2* __restrict__ out, unsigned long long seed,
+                                                           long long start, long long count) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += stride)
+        out[i] = uniform_sample(seed, start + i);
+}
+int launch_synth_uniform(float2* out, unsigned long long seed, long long start, long long count, cudaStream_t s) {
+    if (count <= 0) return 0;
+    synth_uniform_kernel<<<stream_grid(count, 256, 8), 256, 0, s>>>(out, seed, start, count);
+    QDSP_LAUNCH_OK();
+    return 0;
+}
+__device__ __forceinline__ double frac_ratio(long long n, long long f, long long fs) {
+    long long r = ((n % fs) * (f % fs)) % fs;  // |n%fs * f%fs| < 2^63 for fs < 2^31
+    if (r < 0) r += fs;
+    return (double)r / (double)fs;
+}
+__global__ void __launch_bounds__(256) synth_fm_kernel(float2* __restrict__ out, long long start, long long count,
+                                                      long long fs, long long fc, long long fm, double beta,
+                                                      double amp, float noise_amp, unsigned long long noise_seed) {
+    const double two_pi = 6.283185307179586476925286766559;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += stride) {
+        const long long n = start + i;
+        const double ph = two_pi * frac_ratio(n, fc, fs) + beta * sin(two_pi * frac_ratio(n, fm, fs));
+        double sn, cs;
+        sincos(ph, &sn, &cs);
+        float2 v = make_float2((float)(amp * cs), (float)(amp * sn));
+        if (noise_amp != 0.0f) {
+            const float2 u = uniform_sample(noise_seed, n);
+            v.x = __fadd_rn(v.x, __fmul_rn(noise_amp, u.x));
+            v.y = __fadd_rn(v.y, __fmul_rn(noise_amp, u.y));
+        }
+        out[i] = v;
+    }
+}
+int launch_synth_fm(float2* out, long long start, long long count, long long fs, long long fc, long long fm,
+                    double dev, double amp, double noise_amp, unsigned long long noise_seed, cudaStream_t s) {
+    if (count <= 0) return 0;
+    synth_fm_kernel<<<stream_grid(count, 256, 8), 256, 0, s>>>(out, start, count, fs, fc, fm, dev / (double)fm, amp,
+                                                               (float)noise_amp, noise_seed);
+    QDSP_LAUNCH_OK();
+    return 0;
+}
+
+// ---- FP32 roofline denominator: FMA-saturation probe --------------------------------------------------
+template <int PACKED>
+__global__ void __launch_bounds__(512) fp32_peak_kernel(float* sink, int iters, float a, float b) {
+    float2 acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) acc[i] = make_float2(threadIdx.x * 1e-6f + i, i * 0.5f);
+    const float2 aa = make_float2(a, a * 1.0001f), bb = make_float2(b, b * 0.9999f);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            if (PACKED) {
+                acc[i] = __ffma2_rn(acc[i], aa, bb);
+            } else {
+                acc[i].x = fmaf(acc[i].x, aa.x, bb.x);
+                acc[i].y = fmaf(acc[i].y, aa.y, bb.y);
+            }
+        }
+    }
+    float r = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; i++) r += acc[i].x + acc[i].y;
+    if (r == 123.456f) sink[0] = r;
+}
+double run_fp32_peak(int packed, int iters) {
+    float* sink = nullptr;
+    if (cudaMalloc(&sink, 64) != cudaSuccess) return -1.0;
+    const int ctas = sm_count() * 4, threads = 512;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0);
+        if (packed) fp32_peak_kernel<1><<<ctas, threads>>>(sink, iters, 0.999f, 0.001f);
+        else fp32_peak_kernel<0><<<ctas, threads>>>(sink, iters, 0.999f, 0.001f);
+        count_launch();
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1.0; break; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flop = 2.0 * 32.0 * (double)iters * (double)ctas * threads;  // 32 FMA / thread / iter
+        const double tf = flop / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    return best;
+}
+
+}  // namespace qdsp

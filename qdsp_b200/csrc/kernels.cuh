@@ -1,0 +1,67 @@
+// qdsp_b200/csrc/kernels.cuh — host-side launchers of every kernel family (defined in k_*.cu).
+#pragma once
+#include "internal.cuh"
+
+namespace qdsp {
+
+// Per-channel NCO constants on the device: phase(n_abs) = init + step * n_abs (turns * 2^64).
+struct NcoDev {
+    uint64_t init;
+    uint64_t step;
+};
+
+// ---- k_generic.cu -------------------------------------------------------------------------------
+template <typename T>
+int launch_generic_resamp(const T* hist, int H, const T* in, const float* phases_dev, int TPP, int lead,
+                          const Partition& part, T* out, cudaStream_t s);
+int launch_schedule(const Partition& part, int* phase_dev, long long* index_dev, cudaStream_t s);
+// nch channels (grid.z); audio is [nch][out_stride], iq optional [nch][out_stride];
+// demod_state is [2][nch] ping-pong (read slot `st_in`, write the other).
+int launch_generic_vfofm(const float2* hist, int H, const float2* in, const float* phases_dev, int TPP,
+                         const Partition& part, const NcoDev* nco, long long abs0, int nch, float phasor_speed,
+                         const float* demod_in, float* demod_out, float* audio, float2* iq, long long out_stride,
+                         cudaStream_t s);
+
+// ---- k_elementwise.cu ---------------------------------------------------------------------------
+int launch_xlator(const float2* in, float2* out, long long count, uint64_t phase0, uint64_t step, float2 inc1,
+                  float2 inc2, float2 inc3, cudaStream_t s);
+int launch_fmdemod(const float2* in, void* out, long long count, float phasor_speed, const float* state_in,
+                   float* state_out, int stereo, cudaStream_t s);
+int launch_power_decim(const float2* in, float2* out, long long n_out, int copy_only, cudaStream_t s);
+int launch_synth_uniform(float2* out, unsigned long long seed, long long start, long long count, cudaStream_t s);
+int launch_synth_fm(float2* out, long long start, long long count, long long fs, long long fc, long long fm,
+                    double dev, double amp, double noise_amp, unsigned long long noise_seed, cudaStream_t s);
+double run_fp32_peak(int packed, int iters);
+
+// ---- k_decim.cu: column-parallel decimating FIR (I = 1, even D), optional NCO + FM demod --------
+struct DecimPlan;  // opaque, owned by the handle
+DecimPlan* decim_plan_create(const float* taps, int T, int D);
+void decim_plan_destroy(DecimPlan* p);
+bool decim_plan_supported(int T, int interp, int decim);
+// mode: 0 = cf32 resampler output; 1 = fused NCO prologue + FM demod epilogue (audio [+ iq])
+int launch_decim(DecimPlan* plan, const float2* hist, int H, const float2* in, const Partition& part, int mode,
+                 const NcoDev* nco, long long abs0, int nch, float phasor_speed, const float* demod_in,
+                 float* demod_out, float2* out_iq, float* audio, long long out_stride, cudaStream_t s);
+
+// ---- k_fir.cu: register-blocked dense FIR (cf32, D = 1) -----------------------------------------
+struct FirPlan;
+FirPlan* fir_plan_create(const float* taps, int T);
+void fir_plan_destroy(FirPlan* p);
+int launch_fir_dense(FirPlan* plan, const float2* hist, int H, const float2* in, long long count, int lead,
+                     float2* out, cudaStream_t s);
+
+// ---- k_recurrent.cu -----------------------------------------------------------------------------
+int launch_deemp(const float2* in, float2* out, long long count, float alpha, float* state, void* scratch,
+                 size_t scratch_bytes, cudaStream_t s);
+int launch_agc(const float* in, float* out, const Partition& part, float corrected_fall_rate, float* level_state,
+               float* blockmax_scratch, float* level_scratch, cudaStream_t s);
+int launch_cagc(const float2* in, float2* out, long long count, float set_point, float max_gain, float rate,
+                float* gain_state, void* scratch, size_t scratch_bytes, cudaStream_t s);
+int launch_ffagc(const void* hist, int H, const void* in, void* out, long long n_valid, int is_complex,
+                 cudaStream_t s);
+int launch_costas(const float2* in, float2* out, long long count, int order, float alpha, float beta, float* state,
+                  int chunk, int warmup, void* scratch, size_t scratch_bytes, float* residual_dev, cudaStream_t s);
+size_t scan_scratch_bytes(long long count);
+size_t costas_scratch_bytes(long long count, int chunk);
+
+}  // namespace qdsp

@@ -84,3 +84,12 @@ def qpsk_cf32(seed: int, start: int, count: int, sps: int = 4, freq_off: float =
     amp = 1.0 + am_depth * np.sin(2.0 * np.pi * (n % am_period) / am_period)
     sig = amp * const * np.exp(1j * freq_off * n.astype(np.float64))
     return sig.astype(np.complex64) + np.float32(sigma) * uniform_cf32(seed, start, count)
+
+
+def bpsk_cf32(seed: int, start: int, count: int, sps: int = 4, freq_off: float = 0.01, sigma: float = 0.07) -> np.ndarray:
+    """BPSK (+-1) symbols held for `sps` samples, rotated by freq_off rad/sample, + sigma*U noise."""
+    n = np.arange(start, start + count, dtype=np.int64)
+    sym = _splitmix64((np.uint64(seed + 77) << np.uint64(40)) ^ (n // sps).astype(np.uint64))
+    const = 1.0 - 2.0 * (sym & np.uint64(1)).astype(np.float64)
+    sig = const * np.exp(1j * freq_off * n.astype(np.float64))
+    return sig.astype(np.complex64) + np.float32(sigma) * uniform_cf32(seed, start, count)

@@ -1,0 +1,62 @@
+"""Seeded parity cases shared by tools/make_golden.py (which runs the UNMODIFIED reference on them and
+commits the outputs to tests/golden/), tests/test_oracle.py (C restatement vs those outputs) and
+tests/test_gpu_parity.py (CUDA path vs both). Sizes are small enough that the fixture file stays small."""
+import numpy as np
+
+from qdsp_b200 import synth
+
+FS = 2.4e6
+CASES = {
+    # config 1a: complex FIR, 127 taps (BlackmanWindow(300e3, 4*fs/127, fs)), ragged blocks
+    "fir127": dict(kind="fir", win=(300e3, 4 * FS / 127, FS), src=("uniform", 1, 0, 6000), block=[2048, 1000, 2952]),
+    "fir127_f32": dict(kind="fir_f32", win=(300e3, 4 * FS / 127, FS), src=("uniform_f32", 11, 0, 5000), block=1024),
+    # config 1b: the same window through PolyphaseResampler fs -> fs/4 (I=1, D=4)
+    "decim4": dict(kind="resamp", win=(300e3, 4 * FS / 127, FS), in_sr=FS, out_sr=FS / 4, src=("uniform", 1, 0, 16384), block=4096),
+    "decim4_ragged": dict(kind="resamp", win=(300e3, 4 * FS / 127, FS), in_sr=FS, out_sr=FS / 4, src=("uniform", 1, 0, 9001), block=[1001, 4, 3, 0, 4095, 3898]),
+    # genuinely rational: 250 kS/s -> 48 kS/s => I=24, D=125, 999 taps, TPP=42 (VFO-style window)
+    "rational": dict(kind="resamp", win=(24e3, 24e3, 250e3), in_sr=250e3, out_sr=48e3, vfo_style=True, src=("uniform", 7, 0, 10000), block=[1000, 777, 4096, 1001, 3126]),
+    "rational_f32": dict(kind="resamp_f32", win=(3e3, 3e3, 48e3), in_sr=48e3, out_sr=44.1e3, src=("uniform_f32", 8, 0, 6000), block=[1470, 1471, 3059]),
+    "interp": dict(kind="resamp", win=(10e3, 5e3, 48e3), in_sr=48e3, out_sr=192e3, src=("uniform", 9, 0, 3000), block=1000),
+    "power_decim1": dict(kind="power_decim", power=1, src=("uniform", 12, 0, 4096), block=1024),
+    "power_decim3": dict(kind="power_decim", power=3, src=("uniform", 12, 0, 4096), block=1024),
+    # NCO translator alone (float recursive phasor in the reference: short enough that drift is < 1e-5)
+    "xlator": dict(kind="xlator", fs=FS, freq=-250e3, src=("uniform", 2, 0, 3000), block=[1000, 777, 1223]),
+    "fm": dict(kind="fm", fs=48e3, dev=5e3, src=("fm48k", 0, 5000), block=[1024, 1, 3975]),
+    "fm_stereo": dict(kind="fm_stereo", fs=48e3, dev=5e3, src=("fm48k", 0, 2000), block=1000),
+    # VFO alone and config 2's fused chain: 2.4 MS/s -> 48 kS/s (401 taps, I=1, D=50) + FloatFMDemod
+    "vfo": dict(kind="vfo", offset=250e3, in_sr=FS, out_sr=48e3, bw=48e3, src=("cfg2", 0, 40000), block=10000),
+    "vfo_fm": dict(kind="vfo_fm", offset=250e3, in_sr=FS, out_sr=48e3, bw=48e3, dev=5e3, src=("cfg2", 0, 81920), block=8192 * 5),
+    "vfo_fm_ragged": dict(kind="vfo_fm", offset=250e3, in_sr=FS, out_sr=48e3, bw=48e3, dev=5e3, src=("cfg2", 0, 50021), block=[10000, 7777, 49, 0, 51, 20001, 12143]),
+    # config 4 in miniature: 4 channels off one wideband stream (6.144 MS/s -> 48 kS/s: D=128, 1025 taps)
+    "channelizer": dict(kind="channelizer", offsets=[-360e3, -120e3, 120e3, 360e3], in_sr=6.144e6, out_sr=48e3, bw=48e3, dev=5e3, src=("cfg4mini", 0, 65536), block=16384),
+    # config 5: recurrent blocks
+    "deemp": dict(kind="deemp", fs=48e3, tau=50e-6, src=("uniform", 5, 0, 6000), block=[1000, 5000]),
+    "agc": dict(kind="agc", fall=20.0, fs=48e3, src=("uniform_f32", 6, 0, 8000), block=[1000, 3000, 4000]),
+    "cagc": dict(kind="cagc", set_point=1.0, max_gain=65535.0, rate=1e-3, src=("qpsk_am", 21, 0, 8000), block=4000),
+    "ffagc": dict(kind="ffagc", src=("qpsk_am", 22, 0, 6000), block=[500, 600, 2000, 2900]),
+    "costas4": dict(kind="costas", order=4, bw=0.004, src=("qpsk", 23, 0, 8000), block=4000),
+    "costas2": dict(kind="costas", order=2, bw=0.004, src=("bpsk", 24, 0, 8000), block=4000),
+    "costas8": dict(kind="costas", order=8, bw=0.004, src=("qpsk", 25, 0, 4000), block=4000),
+}
+
+
+def make_input(c) -> np.ndarray:
+    src = c["src"]
+    k = src[0]
+    if k == "uniform":
+        return synth.uniform_cf32(src[1], src[2], src[3])
+    if k == "uniform_f32":
+        return synth.uniform_f32(src[1], src[2], src[3])
+    if k == "cfg2":
+        return synth.cfg2_input(src[1], src[2])
+    if k == "fm48k":  # an FM signal already at 48 kS/s (demod-only cases)
+        return synth.fm_cf32(src[1], src[2], 48_000, 3_000, 400, 5e3, 0.7) + np.float32(0.01) * synth.uniform_cf32(3, src[1], src[2])
+    if k == "cfg4mini":
+        return synth.cfg4_input(src[1], src[2], nch=4, fs=6_144_000, spacing=240_000)
+    if k == "qpsk":
+        return synth.qpsk_cf32(src[1], src[2], src[3])
+    if k == "bpsk":
+        return synth.bpsk_cf32(src[1], src[2], src[3])
+    if k == "qpsk_am":
+        return synth.qpsk_cf32(src[1], src[2], src[3], am_depth=0.5, am_period=3000)
+    raise ValueError(k)

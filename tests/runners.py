@@ -1,0 +1,171 @@
+"""Run one tests/cases.py case through (a) the plain-C oracle restatement, (b) the CUDA product path."""
+import numpy as np
+
+from oracle import loader
+
+
+def _stereo(x):
+    return np.ascontiguousarray(x).view(np.float32).reshape(-1, 2)
+
+
+def run_port(c, x):
+    """Returns (output, out_counts or None) from oracle/port.c."""
+    P = loader.port()
+    k = c["kind"]
+    if k == "fir":
+        return P.fir_cf32(P.blackman_taps(*c["win"]), x), None
+    if k == "fir_f32":
+        return P.fir_f32(P.blackman_taps(*c["win"]), x), None
+    if k in ("resamp", "resamp_f32"):
+        i, d = P.rates_to_ratio(c["in_sr"], c["out_sr"])
+        cutoff, tw, wfs = c["win"]
+        if c.get("vfo_style"):
+            wfs = float(np.float32(c["in_sr"]) * np.float32(i))
+        taps = P.blackman_taps(cutoff, tw, wfs, factor=float(i))
+        fn = P.resamp_cf32 if k == "resamp" else P.resamp_f32
+        y, oc = fn(taps, i, d, x, c["block"])
+        return y, oc
+    if k == "power_decim":
+        return P.power_decim(c["power"], x, c["block"])
+    if k == "xlator":
+        inc = P.xlator_phase_delta(c["fs"], c["freq"])
+        y, _ = P.rotator(x, inc, 1 + 0j, c["block"])
+        return y, None
+    if k == "fm":
+        return P.fm_demod(c["fs"], c["dev"], x), None
+    if k == "fm_stereo":
+        y = P.fm_demod(c["fs"], c["dev"], x)
+        return np.stack([y, y], axis=1), None
+    if k == "vfo":
+        a, oc, iq = P.vfo_fm(c["offset"], c["in_sr"], c["out_sr"], c["bw"], 5e3, x, c["block"], want_iq=True)
+        return iq, oc
+    if k == "vfo_fm":
+        return P.vfo_fm(c["offset"], c["in_sr"], c["out_sr"], c["bw"], c["dev"], x, c["block"])
+    if k == "channelizer":
+        rows = [P.vfo_fm(o, c["in_sr"], c["out_sr"], c["bw"], c["dev"], x, c["block"])[0] for o in c["offsets"]]
+        return np.stack(rows), None
+    if k == "deemp":
+        return P.deemp(c["fs"], c["tau"], _stereo(x)).reshape(-1).view(np.complex64), None
+    if k == "agc":
+        return P.agc(c["fall"], c["fs"], x, c["block"]), None
+    if k == "cagc":
+        return P.complex_agc(c["set_point"], c["max_gain"], c["rate"], x), None
+    if k == "ffagc":
+        return P.ff_agc(x), None
+    if k == "costas":
+        return P.costas(c["order"], c["bw"], x)[0], None
+    raise ValueError(k)
+
+
+def run_gpu(c, x, variant=0):
+    """Returns (output, out_counts or None) from libqdsp_b200.so through the block mirror."""
+    from qdsp_b200 import blocks as B
+
+    k = c["kind"]
+    if k in ("fir", "fir_f32"):
+        f = B.FIR(B.BlackmanWindow(*c["win"]), np.complex64 if k == "fir" else np.float32)
+        f.set_variant(variant)
+        # feed block by block like the reference's run() calls (state carried in the handle)
+        outs, off = [], 0
+        sizes = loader.as_blocks(len(x), c["block"])
+        for s in sizes:
+            outs.append(f.process(x[off:off + s]))
+            off += s
+        return np.concatenate(outs), None
+    if k in ("resamp", "resamp_f32"):
+        cutoff, tw, wfs = c["win"]
+        win = B.BlackmanWindow(cutoff, tw, wfs)
+        if c.get("vfo_style"):
+            i, _ = B.rates_to_ratio(c["in_sr"], c["out_sr"])
+            win.setSampleRate(np.float32(c["in_sr"]) * np.float32(i))
+        r = B.PolyphaseResampler(win, c["in_sr"], c["out_sr"], np.complex64 if k == "resamp" else np.float32)
+        r.set_variant(variant)
+        y = r.process(x, c["block"])
+        return y, r.last_out_counts
+    if k == "power_decim":
+        d = B.PowerDecimator(c["power"])
+        sizes = loader.as_blocks(len(x), c["block"])
+        outs, oc, off = [], [], 0
+        for s in sizes:
+            y = d.process(x[off:off + s])
+            outs.append(y)
+            oc.append(len(y))
+            off += s
+        return np.concatenate(outs), np.asarray(oc, np.int32)
+    if k == "xlator":
+        xl = B.FrequencyXlator(c["fs"], c["freq"])
+        sizes = loader.as_blocks(len(x), c["block"])
+        outs, off = [], 0
+        for s in sizes:
+            outs.append(xl.process(x[off:off + s]))
+            off += s
+        return np.concatenate(outs), None
+    if k in ("fm", "fm_stereo"):
+        dm = (B.FloatFMDemod if k == "fm" else B.FMDemod)(c["fs"], c["dev"])
+        sizes = loader.as_blocks(len(x), c["block"])
+        outs, off = [], 0
+        for s in sizes:
+            outs.append(dm.process(x[off:off + s]))
+            off += s
+        y = np.concatenate(outs)
+        if k == "fm_stereo":
+            y = y.view(np.float32).reshape(-1, 2)
+        return y, None
+    if k == "vfo":
+        v = B.VFOFM(c["offset"], c["in_sr"], c["out_sr"], c["bw"], 5e3)
+        v.set_variant(variant)
+        v.want_iq = True
+        v.process(x, c["block"])
+        return v.last_iq, v.last_out_counts
+    if k == "vfo_fm":
+        v = B.VFOFM(c["offset"], c["in_sr"], c["out_sr"], c["bw"], c["dev"])
+        v.set_variant(variant)
+        y = v.process(x, c["block"])
+        return y, v.last_out_counts
+    if k == "channelizer":
+        ch = B.Channelizer(c["offsets"], c["in_sr"], c["out_sr"], c["bw"], c["dev"])
+        ch.set_variant(variant)
+        return ch.process(x, c["block"]), None
+    if k == "deemp":
+        d = B.BFMDeemp(c["fs"], c["tau"])
+        sizes = loader.as_blocks(len(x), c["block"])
+        outs, off = [], 0
+        for s in sizes:
+            outs.append(d.process(x[off:off + s]))
+            off += s
+        return np.concatenate(outs), None
+    if k == "agc":
+        return B.AGC(c["fall"], c["fs"]).process(x, c["block"]), None
+    if k == "cagc":
+        g = B.ComplexAGC(c["set_point"], c["max_gain"], c["rate"])
+        sizes = loader.as_blocks(len(x), c["block"])
+        outs, off = [], 0
+        for s in sizes:
+            outs.append(g.process(x[off:off + s]))
+            off += s
+        return np.concatenate(outs), None
+    if k == "ffagc":
+        g = B.FeedForwardAGC()
+        sizes = loader.as_blocks(len(x), c["block"])
+        outs, off = [], 0
+        for s in sizes:
+            outs.append(g.process(x[off:off + s]))
+            off += s
+        return np.concatenate(outs), None
+    if k == "costas":
+        pl = B.CostasLoop(c["order"], c["bw"])
+        pl.set_chunking(c.get("chunk", 0), c.get("warmup", 0))
+        sizes = loader.as_blocks(len(x), c["block"])
+        outs, off = [], 0
+        for s in sizes:
+            outs.append(pl.process(x[off:off + s]))
+            off += s
+        return np.concatenate(outs), None
+    raise ValueError(k)
+
+
+def rel_l2(a, b):
+    a = np.asarray(a).astype(np.complex128 if np.iscomplexobj(a) else np.float64)
+    b = np.asarray(b).astype(a.dtype)
+    den = np.linalg.norm(b)
+    return float(np.linalg.norm(a - b) / den) if den > 0 else float(np.linalg.norm(a - b))
