@@ -147,6 +147,10 @@ int qdsp_vfofm_set_variant(qdsp_vfofm* h, int variant);
 int qdsp_vfofm_seek(qdsp_vfofm* h, long long start);
 int qdsp_vfofm_import_tail(qdsp_vfofm* h, const void* tail_dev, int src_device, qdsp_stream_t s);
 int qdsp_vfofm_history_len(qdsp_vfofm* h);
+/* bench hook: bracket the dominant kernel of each process call with CUDA events on the caller's
+ * stream; kernel_ms() synchronises and returns the last launch's device time */
+int qdsp_vfofm_enable_timing(qdsp_vfofm* h, int on);
+double qdsp_vfofm_kernel_ms(qdsp_vfofm* h);
 
 /* ---- channelizer: nch x [VFO -> FloatFMDemod] off one Splitter (routing.h:47-57) ------------ */
 typedef struct qdsp_channelizer qdsp_channelizer;

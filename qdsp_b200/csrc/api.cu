@@ -437,6 +437,9 @@ struct qdsp_channelizer {
     cudaEvent_t ev_done[2] = {nullptr, nullptr};
     cudaStream_t copy_stream = nullptr;
     size_t stage_samples = 0;
+    // bench hook: events around the dominant kernel
+    bool timing = false;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
 
     int upload_nco() {
         std::vector<NcoDev> v(nch);
@@ -487,6 +490,7 @@ struct qdsp_channelizer {
         const float* din = demod.p + (size_t)cur * nch;
         float* dout = demod.p + (size_t)(cur ^ 1) * nch;
         int rc;
+        if (timing) QDSP_CUDA_OK(cudaEventRecord(ev_k0, s));
         if (plan && variant != 1)
             rc = launch_decim(plan, (const float2*)hist.ptr(), hist.H, (const float2*)in_dev, part, 1, nco_dev,
                               abs_pos, nch, phasor_speed, din, dout, (float2*)iq, audio, out_stride, s);
@@ -495,6 +499,7 @@ struct qdsp_channelizer {
                                       nco_dev, abs_pos, nch, phasor_speed, din, dout, audio, (float2*)iq, out_stride,
                                       s);
         if (rc != 0) return -1;
+        if (timing) QDSP_CUDA_OK(cudaEventRecord(ev_k1, s));
         if (part.total_out > 0) cur ^= 1;
         if (hist.advance(in_dev, count, s) != 0) return -1;
         abs_pos += count;
@@ -511,6 +516,8 @@ struct qdsp_channelizer {
             if (ev_done[i]) cudaEventDestroy(ev_done[i]);
         }
         if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (ev_k0) cudaEventDestroy(ev_k0);
+        if (ev_k1) cudaEventDestroy(ev_k1);
     }
 };
 struct qdsp_vfofm {
@@ -628,6 +635,21 @@ int qdsp_vfofm_import_tail(qdsp_vfofm* h, const void* tail_dev, int src_device, 
     return import_tail_impl(h->c.hist, tail_dev, src_device, as_stream(s));
 }
 int qdsp_vfofm_history_len(qdsp_vfofm* h) { return h->c.hist.H; }
+int qdsp_vfofm_enable_timing(qdsp_vfofm* h, int on) {
+    if (on && !h->c.ev_k0) {
+        QDSP_CUDA_OK(cudaEventCreate(&h->c.ev_k0));
+        QDSP_CUDA_OK(cudaEventCreate(&h->c.ev_k1));
+    }
+    h->c.timing = on != 0;
+    return 0;
+}
+double qdsp_vfofm_kernel_ms(qdsp_vfofm* h) {
+    if (!h->c.ev_k0) return -1.0;
+    if (cudaEventSynchronize(h->c.ev_k1) != cudaSuccess) return -1.0;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->c.ev_k0, h->c.ev_k1) != cudaSuccess) return -1.0;
+    return (double)ms;
+}
 
 qdsp_channelizer* qdsp_channelizer_create(int nch, const float* offsets, float inSampleRate, float outSampleRate,
                                           float bandWidth, float deviation) {

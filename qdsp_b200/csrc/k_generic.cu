@@ -39,7 +39,9 @@ __device__ __forceinline__ T generic_output(const VStream<T>& xs, const float* _
                 const float2 ph = phasor_from_turns(nco_phase0 + nco_step * (uint64_t)(base + t));
                 v = cmul_exact(v, ph);
             }
-            acc0 = Elem<T>::mac(v, h[t], acc0);
+            // same even/odd accumulator split as the fast path: results do not depend on the path
+            if (t & 1) acc1 = Elem<T>::mac(v, h[t], acc1);
+            else acc0 = Elem<T>::mac(v, h[t], acc0);
         }
     }
     return Elem<T>::add(acc0, acc1);

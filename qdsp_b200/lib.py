@@ -96,6 +96,8 @@ SIGNATURES = {
     "qdsp_vfofm_seek": (_i, [_vp, _ll]),
     "qdsp_vfofm_import_tail": (_i, [_vp, _vp, _i, _vp]),
     "qdsp_vfofm_history_len": (_i, [_vp]),
+    "qdsp_vfofm_enable_timing": (_i, [_vp, _i]),
+    "qdsp_vfofm_kernel_ms": (_d, [_vp]),
     "qdsp_channelizer_create": (_vp, [_i, _fp, _f, _f, _f, _f]),
     "qdsp_channelizer_destroy": (None, [_vp]),
     "qdsp_channelizer_design": (_i, [_vp, _ip, _ip, _ip]),
