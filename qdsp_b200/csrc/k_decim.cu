@@ -17,6 +17,7 @@
 // Column partial sums are exchanged through a small double-buffered shared array and reduced by
 // 8-lane groups; the epilogue applies fast_arctan2 + phase difference on chip, so neither the
 // translated nor the resampled IQ ever reaches HBM (unless the caller asks for the IQ).
+#include <stdlib.h>
 #include <new>
 #include <vector>
 #include "internal.cuh"
@@ -102,28 +103,36 @@ __device__ float2 direct_output_warp(const DecimArgs& a, long long win_start, ui
     return acc;
 }
 
-template <int Q, int R, bool ROT, bool DEMOD, int MAXT, int MINB>
+// packed f32x2 helpers for the two-column phasor recurrence
+__device__ __forceinline__ float2 neg2(float2 v) { return make_float2(-v.x, -v.y); }
+
+template <int Q, int DT, bool ROT, bool DEMOD, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
+    constexpr int R = 3;            // rows per stage per segment
+    constexpr int NS = Q / R;       // stages per super-iteration == ring depth: slot index is static
     constexpr int LEAD = DEMOD ? 1 : 0;
+    static_assert(Q % R == 0 && NS >= 2, "Q must be a multiple of 3, at least 6");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int D = a.D, P = a.P, NSEG = a.NSEG, NSTAGE = a.NSTAGE, L = a.L;
-    const int NT = blockDim.x;
+    const int D = DT ? DT : a.D;
+    const int P = D / 2, NSEG = a.NSEG, L = a.L;
     const int t = threadIdx.x;
     const int b = blockIdx.y, ch = blockIdx.z;
     const BlkInfo bi = a.part.get(b);
     const int k0 = blockIdx.x * (NSEG * L);
     if (k0 >= bi.out_count) return;
 
-    // ---- shared memory carve-up --------------------------------------------------------------
-    const int chunk_elems = R * D;                        // per segment per stage
-    const size_t stage_bytes = (size_t)NSEG * chunk_elems * sizeof(float2);
+    // ---- shared memory carve-up (byte offsets from the dynamic base) ---------------------------
+    const int chunk_elems = R * D;                                   // per segment per stage
+    const uint32_t chunk_bytes = (uint32_t)chunk_elems * 8u;
+    const uint32_t stage_bytes = (uint32_t)NSEG * chunk_bytes;
     const int Ppad = P | 1;
+    const uint32_t pbuf_half = (uint32_t)(NSEG * R * Ppad) * 8u;     // one parity of the partial buffer
     float2* X = reinterpret_cast<float2*>(smem_raw);
-    float2* Pbuf = reinterpret_cast<float2*>(smem_raw + (size_t)NSTAGE * stage_bytes);  // [2][NSEG*R][Ppad]
-    float* s_ang = reinterpret_cast<float*>(Pbuf + 2 * NSEG * R * Ppad);                  // [NSEG][L+LEAD]
+    float2* Pbuf = reinterpret_cast<float2*>(smem_raw + NS * stage_bytes);                   // [2][NSEG*R][Ppad]
+    float* s_ang = reinterpret_cast<float*>(smem_raw + NS * stage_bytes + 2 * pbuf_half);    // [NSEG][L+LEAD]
     uint64_t* mbar = reinterpret_cast<uint64_t*>(
-        (reinterpret_cast<uintptr_t>(s_ang + NSEG * (L + LEAD)) + 15) & ~(uintptr_t)15);   // [NSTAGE]
-    float* s_misc = reinterpret_cast<float*>(mbar + NSTAGE);                              // [0]=override angle
+        (reinterpret_cast<uintptr_t>(s_ang + NSEG * (L + LEAD)) + 15) & ~(uintptr_t)15);      // [NS]
+    float* s_misc = reinterpret_cast<float*>(mbar + NS);                                     // [0]=override angle
 
     // ---- thread roles ------------------------------------------------------------------------
     const int seg = t / P;
@@ -136,7 +145,17 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
     // rows this CTA really needs: its fullest segment (segment 0) has min(L, out_count - k0) outputs
     const int need = (bi.out_count - k0 < L ? bi.out_count - k0 : L) + LEAD + Q - 1;
     const int nsup = (need + Q - 1) / Q < a.NSUP ? (need + Q - 1) / Q : a.NSUP;
-    const int nst = nsup * (Q / R);
+    const int nst = nsup * NS;
+    // producer bookkeeping: stages [fast_lo, fast_hi) of this segment are plain TMA bulk copies; stages
+    // outside (history before sample 0, ragged end of the caller's buffer) are filled by guarded loads
+    int fast_lo = 0, fast_hi = 0, live_hi = 0;
+    if (seg_active) {
+        live_hi = nst;
+        const long long lo = seg_base >= 0 ? 0 : (-seg_base + chunk_elems - 1) / chunk_elems;
+        const long long hi = a.n_in - seg_base < 0 ? 0 : (a.n_in - seg_base) / chunk_elems;
+        fast_lo = (int)(lo < nst ? lo : nst);
+        fast_hi = (int)(hi < nst ? hi : nst);
+    }
 
     uint64_t nco_step = 0, nco_ph0 = 0;
     if (ROT) {
@@ -145,7 +164,7 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
     }
 
     if (t == 0) {
-        for (int s = 0; s < NSTAGE; s++) mbar_init(&mbar[s], NSEG);
+        for (int s = 0; s < NS; s++) mbar_init(&mbar[s], NSEG);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // leading-angle override of the block's very first output (warp 0)
@@ -172,24 +191,25 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
     }
     __syncthreads();
 
-    // ---- producer: one TMA bulk copy per (segment, stage); guarded fill at the buffer ends ---------
-    auto issue = [&](int it) {
+    // ---- producer: one TMA bulk copy per (segment, stage) -------------------------------------------
+    const float2* gsrc = a.in + seg_base;  // only dereferenced for stages in [fast_lo, fast_hi)
+    float2* xseg = X + (size_t)seg * chunk_elems;
+    auto issue = [&](int it, int slot) {
         if (!in_grid) return;
-        const int slot = it % NSTAGE;
-        const long long start = seg_base + (long long)it * chunk_elems;
-        float2* dst = X + (size_t)slot * NSEG * chunk_elems + (size_t)seg * chunk_elems;
-        const bool live = seg_active && it < nst;
-        const bool fast = live && start >= 0 && start + chunk_elems <= a.n_in;
+        const bool fast = it >= fast_lo && it < fast_hi;
         if (pair == 0) {
             if (fast) {
-                mbar_arrive_expect_tx(&mbar[slot], (uint32_t)(chunk_elems * sizeof(float2)));
-                tma_bulk_g2s(dst, a.in + start, (uint32_t)(chunk_elems * sizeof(float2)), &mbar[slot]);
+                mbar_arrive_expect_tx(&mbar[slot], chunk_bytes);
+                tma_bulk_g2s(reinterpret_cast<unsigned char*>(xseg) + slot * stage_bytes,
+                             gsrc + (size_t)it * chunk_elems, chunk_bytes, &mbar[slot]);
             } else {
                 mbar_arrive(&mbar[slot]);
             }
         }
-        if (live && !fast) {
+        if (!fast && it < live_hi) {
             VStream<float2> xs{a.hist, a.in, a.H};
+            float2* dst = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(xseg) + slot * stage_bytes);
+            const long long start = seg_base + (long long)it * chunk_elems;
             for (int e = pair; e < chunk_elems; e += P) {
                 const long long i = start + e;
                 dst[e] = (i < a.n_in) ? xs.at(i) : make_float2(0.f, 0.f);
@@ -206,97 +226,115 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
 #pragma unroll
         for (int q = 0; q < Q; q++) tp[q] = tt[q * P + pair];
     }
-    float2 p0 = make_float2(1.f, 0.f), p1 = make_float2(1.f, 0.f), w = make_float2(1.f, 0.f);
+    // phasors of the pair's two columns, packed (re, re) / (im, im) so one FFMA2 advances both
+    float2 PR = make_float2(1.f, 1.f), PI = make_float2(0.f, 0.f);
+    float2 wr2 = make_float2(1.f, 1.f), wi2 = make_float2(0.f, 0.f);
     const long long col0 = seg_base + 2 * pair;  // sample index of (row 0, first column of the pair)
-    if (ROT) w = phasor_from_turns(nco_step * (uint64_t)D);
+    if (ROT) {
+        const float2 w = phasor_from_turns(nco_step * (uint64_t)D);
+        wr2 = make_float2(w.x, w.x);
+        wi2 = make_float2(w.y, w.y);
+    }
 
     float2 accRe[Q], accIm[Q];
 #pragma unroll
     for (int q = 0; q < Q; q++) accRe[q] = accIm[q] = make_float2(0.f, 0.f);
 
-    for (int it = 0; it < NSTAGE; it++) issue(it);
+    // my float4 (two adjacent samples) in slot 0, row 0; my partial slot in parity 0, row 0
+    const float4* xme = reinterpret_cast<const float4*>(xseg) + pair;
+    float2* pme = Pbuf + (seg * R) * Ppad + pair;
+    const int row4 = D / 2;  // float4 per row
+
+    // ---- reduction role (8 lanes per output of the stage) ----------------------------------------------
+    const int u = t & 7, o = t >> 3;
+    const bool ovalid = o < NSEG * R;
+    const int so = o / R, ro = o - so * R;
+    const float2* pbr = Pbuf + o * Ppad + u;
+    const bool oseg_active = ovalid && (k0 + so * L < bi.out_count);
+    int j = ro - (Q - 1);                       // output index within the segment at stage 0 (0 = leading)
+    int kout = k0 + so * L - LEAD + j;          // output index within the block
+    float* angrow = s_ang + so * (L + LEAD);
+    float ang_prev = 0.0f;                      // this lane's output angle of the previous stage
+    bool have_prev = false;
+
+    for (int s = 0; s < NS; s++) issue(s, s);
     __syncthreads();
 
-    // ---- reduction of one stage's column partials + epilogue ----------------------------------------
-    auto reduce_stage = [&](int it) {
-        const float2* pb = Pbuf + (size_t)(it & 1) * NSEG * R * Ppad;
-        const int u = t & 7;
-        // warp-uniform trip count: every lane runs the shuffles, out-of-range groups just add zeros
-        for (int ob = (t >> 5) * 4; ob < NSEG * R; ob += (NT >> 5) * 4) {
-            const int o = ob + ((t & 31) >> 3);
-            const bool ovalid = o < NSEG * R;
-            float2 s = make_float2(0.f, 0.f);
-            if (ovalid) {
-                for (int pp = u; pp < P; pp += 8) {
-                    const float2 v = pb[o * Ppad + pp];
-                    s.x += v.x;
-                    s.y += v.y;
-                }
+    auto reduce_stage = [&](int par) {
+        // demod of the output this lane finished one stage ago (its left neighbour's angle is visible now)
+        if (DEMOD && u == 0 && have_prev) {
+            const float prev = angrow[j - R - 1];
+            a.audio[ch * a.out_stride + bi.out_start + (kout - R)] = fm_step_ref(ang_prev, prev, a.phasor_speed);
+            if (bi.out_start + (kout - R) == a.part.total_out - 1) a.demod_out[ch] = ang_prev;
+        }
+        have_prev = false;
+        float2 sacc = make_float2(0.f, 0.f);
+        if (ovalid) {
+            const float2* pb = reinterpret_cast<const float2*>(reinterpret_cast<const unsigned char*>(pbr) + par * pbuf_half);
+            for (int pp = u; pp < P; pp += 8) {
+                const float2 v = pb[pp - u];
+                sacc.x += v.x;
+                sacc.y += v.y;
             }
+        }
 #pragma unroll
-            for (int sh = 4; sh > 0; sh >>= 1) {
-                s.x += __shfl_xor_sync(0xffffffffu, s.x, sh);
-                s.y += __shfl_xor_sync(0xffffffffu, s.y, sh);
-            }
-            if (u == 0 && ovalid) {
-                const int so = o / R, ro = o - so * R;
-                const int j = it * R + ro - (Q - 1);  // output index within the segment (0 = leading)
-                const int k = k0 + so * L - LEAD + j;
-                if (j >= 0 && j < L + LEAD && k < bi.out_count && k0 + so * L < bi.out_count) {
-                    if (DEMOD) {
-                        float ang = fast_arctan2_ref(s.y, s.x);
-                        if (use_override && so == 0 && j == 0) ang = s_misc[0];
-                        s_ang[so * (L + LEAD) + j] = ang;
-                        if (a.out_iq && j >= LEAD) a.out_iq[ch * a.out_stride + bi.out_start + k] = s;
-                    } else {
-                        a.out_iq[ch * a.out_stride + bi.out_start + k] = s;
-                    }
-                }
+        for (int sh = 4; sh > 0; sh >>= 1) {
+            sacc.x += __shfl_xor_sync(0xffffffffu, sacc.x, sh);
+            sacc.y += __shfl_xor_sync(0xffffffffu, sacc.y, sh);
+        }
+        if (u == 0 && oseg_active && j >= 0 && j < L + LEAD && kout < bi.out_count) {
+            if (DEMOD) {
+                float ang = fast_arctan2_ref(sacc.y, sacc.x);
+                if (use_override && so == 0 && j == 0) ang = s_misc[0];
+                angrow[j] = ang;
+                ang_prev = ang;
+                have_prev = j >= LEAD;
+                if (a.out_iq && j >= LEAD) a.out_iq[ch * a.out_stride + bi.out_start + kout] = sacc;
+            } else {
+                a.out_iq[ch * a.out_stride + bi.out_start + kout] = sacc;
             }
         }
-    };
-    auto demod_stage = [&](int it) {
-        if (!DEMOD) return;
-        for (int o = t; o < NSEG * R; o += NT) {
-            const int so = o / R, ro = o - so * R;
-            const int j = it * R + ro - (Q - 1);
-            const int k = k0 + so * L - LEAD + j;
-            if (j >= LEAD && j < L + LEAD && k < bi.out_count) {
-                const float cur = s_ang[so * (L + LEAD) + j], prev = s_ang[so * (L + LEAD) + j - 1];
-                a.audio[ch * a.out_stride + bi.out_start + k] = fm_step_ref(cur, prev, a.phasor_speed);
-                if (bi.out_start + k == a.part.total_out - 1) a.demod_out[ch] = cur;
-            }
-        }
+        j += R;
+        kout += R;
     };
 
-    // ---- main loop: NSUP super-iterations of Q rows (= Q/R stages) ----------------------------------
-    const int rowstride4 = D / 2;  // float4 per row
+    // ---- main loop: nsup super-iterations of Q rows (= NS stages, one ring slot each) ----------------
 #pragma unroll 1
     for (int sup = 0; sup < nsup; sup++) {
         if (ROT && (sup & 3) == 0 && seg_active) {
             // exact phasor re-seed (closed form) every 4*Q rows bounds the recurrence's rounding walk
             const long long i0 = col0 + (long long)sup * Q * D;
-            p0 = phasor_from_turns(nco_ph0 + nco_step * (uint64_t)i0);
-            p1 = phasor_from_turns(nco_ph0 + nco_step * (uint64_t)(i0 + 1));
+            const float2 p0 = phasor_from_turns(nco_ph0 + nco_step * (uint64_t)i0);
+            const float2 p1 = phasor_from_turns(nco_ph0 + nco_step * (uint64_t)(i0 + 1));
+            PR = make_float2(p0.x, p1.x);
+            PI = make_float2(p0.y, p1.y);
         }
+        const uint32_t parity = (uint32_t)(sup & 1);
 #pragma unroll
         for (int i = 0; i < Q; i++) {
-            const int it = sup * (Q / R) + i / R;
-            const int slot = it % NSTAGE;
-            if (i % R == 0) mbar_wait(&mbar[slot], (uint32_t)((it / NSTAGE) & 1));
+            constexpr int dummy = 0;
+            (void)dummy;
+            const int slot = i / R;                 // compile-time after unrolling
+            const int par = (sup * NS + slot) & 1;  // partial-buffer parity of this stage
+            if (i % R == 0) mbar_wait(&mbar[slot], parity);
             if (seg_active) {
-                const float4* xr = reinterpret_cast<const float4*>(X + (size_t)slot * NSEG * chunk_elems +
-                                                                   (size_t)seg * chunk_elems) +
-                                   (i % R) * rowstride4 + pair;
-                const float4 v = *xr;
-                float2 x0 = make_float2(v.x, v.y), x1 = make_float2(v.z, v.w);
+                const float4 v = *reinterpret_cast<const float4*>(
+                    reinterpret_cast<const unsigned char*>(xme + (i % R) * row4) + slot * stage_bytes);
+                float2 RE, IM;
                 if (ROT) {
-                    x0 = cmul(x0, p0);
-                    x1 = cmul(x1, p1);
-                    p0 = cmul(p0, w);
-                    p1 = cmul(p1, w);
+                    // x' = x * p for both columns; results land directly in the packed (col r, col r+1) pairs
+                    RE.x = fmaf(v.x, PR.x, -(v.y * PI.x));
+                    IM.x = fmaf(v.x, PI.x, v.y * PR.x);
+                    RE.y = fmaf(v.z, PR.y, -(v.w * PI.y));
+                    IM.y = fmaf(v.z, PI.y, v.w * PR.y);
+                    // p *= w for both columns in 4 packed ops
+                    const float2 nPR = __ffma2_rn(PI, neg2(wi2), __fmul2_rn(PR, wr2));
+                    PI = __ffma2_rn(PI, wr2, __fmul2_rn(PR, wi2));
+                    PR = nPR;
+                } else {
+                    RE = make_float2(v.x, v.z);
+                    IM = make_float2(v.y, v.w);
                 }
-                const float2 RE = make_float2(x0.x, x1.x), IM = make_float2(x0.y, x1.y);
 #pragma unroll
                 for (int q = 0; q < Q; q++) {
                     const int sl = (i - q + Q) % Q;
@@ -309,30 +347,35 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
                     }
                 }
                 const int e = (i + 1) % Q;  // the output whose last tap (q = Q-1) was just applied
-                Pbuf[(size_t)(it & 1) * NSEG * R * Ppad + (seg * R + (i % R)) * Ppad + pair] =
+                *reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(pme + (i % R) * Ppad) + par * pbuf_half) =
                     make_float2(accRe[e].x + accRe[e].y, accIm[e].x + accIm[e].y);
             }
             if (i % R == R - 1) {
-                __syncthreads();            // stage consumed, partials visible
-                issue(it + NSTAGE);         // refill the slot just drained
-                reduce_stage(it);
-                if (it > 0) demod_stage(it - 1);
+                __syncthreads();                       // stage consumed, partials visible
+                issue((sup + 1) * NS + slot, slot);    // refill the slot just drained
+                reduce_stage(par);
             }
         }
     }
-    __syncthreads();
-    demod_stage(nst - 1);
+    if (DEMOD) {
+        __syncthreads();
+        if (u == 0 && have_prev) {
+            const float prev = angrow[j - R - 1];
+            a.audio[ch * a.out_stride + bi.out_start + (kout - R)] = fm_step_ref(ang_prev, prev, a.phasor_speed);
+            if (bi.out_start + (kout - R) == a.part.total_out - 1) a.demod_out[ch] = ang_prev;
+        }
+    }
 }
 
 // ---- host side -------------------------------------------------------------------------------------
 bool decim_plan_supported(int T, int interp, int decim) {
     if (interp != 1 || (decim & 1) || decim < 8) return false;
     const int Q = (T + 1 + decim - 1) / decim;
-    if (Q > 9 || Q < 2) return false;       // instantiated: Q in {3, 6, 9} (padded up)
+    if (Q > 9 || Q < 2) return false;       // instantiated: Q in {6, 9} (padded up)
     if (decim / 2 > 640) return false;
     return true;
 }
-static int round_q(int Q) { return Q <= 3 ? 3 : Q <= 6 ? 6 : 9; }
+static int round_q(int Q) { return Q <= 6 ? 6 : 9; }
 
 DecimPlan* decim_plan_create(const float* taps, int T, int D) {
     if (!decim_plan_supported(T, 1, D)) return nullptr;
@@ -343,15 +386,18 @@ DecimPlan* decim_plan_create(const float* taps, int T, int D) {
     p->P = D / 2;
     p->Q = round_q((T + 1 + D - 1) / D);
     p->R = 3;
-    p->NSTAGE = 4;
-    // segments per CTA: fill ~416 threads
-    int nseg = 416 / p->P;
+    p->NSTAGE = p->Q / 3;
+    // segments per CTA: ~320 threads (two CTAs per SM with up to 96 registers per thread: no spills); the
+    // reduction role needs 8 lanes per output of a stage, i.e. NT >= 24 * NSEG
+    int nseg = 320 / p->P;
+    if (nseg > 13) nseg = 13;
     if (nseg < 1) nseg = 1;
-    if (nseg > 32) nseg = 32;
     p->NSEG = nseg;
-    p->NT = ((nseg * p->P + 31) / 32) * 32;
+    int nt = nseg * p->P > nseg * 24 ? nseg * p->P : nseg * 24;
+    p->NT = ((nt + 31) / 32) * 32;
     if (p->NT < 64) p->NT = 64;
     p->NSUP = 15;
+    if (const char* e = getenv("QDSP_DECIM_NSUP")) p->NSUP = atoi(e) > 1 ? atoi(e) : 15;
     std::vector<float2> tab((size_t)2 * p->Q * p->P, make_float2(0.f, 0.f));
     for (int pad = 0; pad < 2; pad++)
         for (int q = 0; q < p->Q; q++)
@@ -376,14 +422,14 @@ void decim_plan_destroy(DecimPlan* p) {
     delete p;
 }
 
-template <int Q, bool ROT, bool DEMOD>
+template <int Q, int DT, bool ROT, bool DEMOD>
 static int launch_decim_t(const DecimArgs& a, dim3 grid, int NT, size_t smem, cudaStream_t s) {
-    if (NT <= 448) {
-        auto kern = decim_kernel<Q, 3, ROT, DEMOD, 448, 2>;
+    if (NT <= 320) {
+        auto kern = decim_kernel<Q, DT, ROT, DEMOD, 320, 2>;
         QDSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, NT, smem, s>>>(a);
     } else {
-        auto kern = decim_kernel<Q, 3, ROT, DEMOD, 640, 1>;
+        auto kern = decim_kernel<Q, DT, ROT, DEMOD, 640, 1>;
         QDSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, NT, smem, s>>>(a);
     }
@@ -432,16 +478,16 @@ int launch_decim(DecimPlan* plan, const float2* hist, int H, const float2* in, c
         set_last_error("decim: tile does not fit shared memory (%zu bytes)", smem);
         return -1;
     }
-#define QDSP_DECIM_CASE(QQ)                                                                                   \
-    case QQ:                                                                                                  \
-        return mode == 1 ? launch_decim_t<QQ, true, true>(a, grid, plan->NT, smem, s)                         \
-                         : launch_decim_t<QQ, false, false>(a, grid, plan->NT, smem, s);
-    switch (plan->Q) {
-        QDSP_DECIM_CASE(3)
-        QDSP_DECIM_CASE(6)
-        QDSP_DECIM_CASE(9)
-    }
-#undef QDSP_DECIM_CASE
+    const bool fused = mode == 1;
+    if (plan->Q == 9 && plan->D == 50)
+        return fused ? launch_decim_t<9, 50, true, true>(a, grid, plan->NT, smem, s)
+                     : launch_decim_t<9, 50, false, false>(a, grid, plan->NT, smem, s);
+    if (plan->Q == 9)
+        return fused ? launch_decim_t<9, 0, true, true>(a, grid, plan->NT, smem, s)
+                     : launch_decim_t<9, 0, false, false>(a, grid, plan->NT, smem, s);
+    if (plan->Q == 6)
+        return fused ? launch_decim_t<6, 0, true, true>(a, grid, plan->NT, smem, s)
+                     : launch_decim_t<6, 0, false, false>(a, grid, plan->NT, smem, s);
     set_last_error("decim: unsupported Q=%d", plan->Q);
     return -1;
 }
