@@ -106,15 +106,16 @@ __device__ float2 direct_output_warp(const DecimArgs& a, long long win_start, ui
 // packed f32x2 helpers for the two-column phasor recurrence
 __device__ __forceinline__ float2 neg2(float2 v) { return make_float2(-v.x, -v.y); }
 
-template <int Q, int DT, bool ROT, bool DEMOD, int MAXT, int MINB>
+template <int Q, int DT, int NSEGT, bool ROT, bool DEMOD, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
     constexpr int R = 3;            // rows per stage per segment
     constexpr int NS = Q / R;       // stages per super-iteration == ring depth: slot index is static
     constexpr int LEAD = DEMOD ? 1 : 0;
     static_assert(Q % R == 0 && NS >= 2, "Q must be a multiple of 3, at least 6");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int D = DT ? DT : a.D;
-    const int P = D / 2, NSEG = a.NSEG, L = a.L;
+    const int D = DT ? DT : a.D;                 // compile-time in the specialised instantiations:
+    const int NSEG = NSEGT ? NSEGT : a.NSEG;     // all shared-memory offsets fold into immediates
+    const int P = D / 2, L = a.L;
     const int t = threadIdx.x;
     const int b = blockIdx.y, ch = blockIdx.z;
     const BlkInfo bi = a.part.get(b);
@@ -127,11 +128,11 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
     const uint32_t stage_bytes = (uint32_t)NSEG * chunk_bytes;
     const int Ppad = P | 1;
     const uint32_t pbuf_half = (uint32_t)(NSEG * R * Ppad) * 8u;     // one parity of the partial buffer
+    const int LL = L + LEAD;                                         // outputs kept per segment
     float2* X = reinterpret_cast<float2*>(smem_raw);
     float2* Pbuf = reinterpret_cast<float2*>(smem_raw + NS * stage_bytes);                   // [2][NSEG*R][Ppad]
-    float* s_ang = reinterpret_cast<float*>(smem_raw + NS * stage_bytes + 2 * pbuf_half);    // [NSEG][L+LEAD]
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(
-        (reinterpret_cast<uintptr_t>(s_ang + NSEG * (L + LEAD)) + 15) & ~(uintptr_t)15);      // [NS]
+    float2* ybuf = reinterpret_cast<float2*>(smem_raw + NS * stage_bytes + 2 * pbuf_half);   // [NSEG][LL]
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(ybuf + NSEG * LL);                          // [NS]
     float* s_misc = reinterpret_cast<float*>(mbar + NS);                                     // [0]=override angle
 
     // ---- thread roles ------------------------------------------------------------------------
@@ -241,36 +242,26 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
     for (int q = 0; q < Q; q++) accRe[q] = accIm[q] = make_float2(0.f, 0.f);
 
     // my float4 (two adjacent samples) in slot 0, row 0; my partial slot in parity 0, row 0
-    const float4* xme = reinterpret_cast<const float4*>(xseg) + pair;
-    float2* pme = Pbuf + (seg * R) * Ppad + pair;
-    const int row4 = D / 2;  // float4 per row
+    const unsigned char* xme = reinterpret_cast<const unsigned char*>(reinterpret_cast<const float4*>(xseg) + pair);
+    unsigned char* pme = reinterpret_cast<unsigned char*>(Pbuf + (seg * R) * Ppad + pair);
+    const uint32_t row_bytes = (uint32_t)D * 8u;
+    const uint32_t prow_bytes = (uint32_t)Ppad * 8u;
 
-    // ---- reduction role (8 lanes per output of the stage) ----------------------------------------------
+    // ---- reduction role: 8 lanes sum one output's P column partials, lane 0 parks y in ybuf ------------
     const int u = t & 7, o = t >> 3;
     const bool ovalid = o < NSEG * R;
     const int so = o / R, ro = o - so * R;
-    const float2* pbr = Pbuf + o * Ppad + u;
-    const bool oseg_active = ovalid && (k0 + so * L < bi.out_count);
-    int j = ro - (Q - 1);                       // output index within the segment at stage 0 (0 = leading)
-    int kout = k0 + so * L - LEAD + j;          // output index within the block
-    float* angrow = s_ang + so * (L + LEAD);
-    float ang_prev = 0.0f;                      // this lane's output angle of the previous stage
-    bool have_prev = false;
+    const unsigned char* pbr = reinterpret_cast<const unsigned char*>(Pbuf + o * Ppad + u);
+    float2* yrow = ybuf + so * LL + (ro - (Q - 1));  // + it*R = this lane's output slot at stage it
+    const bool ylane = ovalid && u == 0 && (k0 + so * L < bi.out_count);
 
     for (int s = 0; s < NS; s++) issue(s, s);
     __syncthreads();
 
-    auto reduce_stage = [&](int par) {
-        // demod of the output this lane finished one stage ago (its left neighbour's angle is visible now)
-        if (DEMOD && u == 0 && have_prev) {
-            const float prev = angrow[j - R - 1];
-            a.audio[ch * a.out_stride + bi.out_start + (kout - R)] = fm_step_ref(ang_prev, prev, a.phasor_speed);
-            if (bi.out_start + (kout - R) == a.part.total_out - 1) a.demod_out[ch] = ang_prev;
-        }
-        have_prev = false;
+    auto reduce_stage = [&](int it, int par) {
         float2 sacc = make_float2(0.f, 0.f);
         if (ovalid) {
-            const float2* pb = reinterpret_cast<const float2*>(reinterpret_cast<const unsigned char*>(pbr) + par * pbuf_half);
+            const float2* pb = reinterpret_cast<const float2*>(pbr + par * pbuf_half);
             for (int pp = u; pp < P; pp += 8) {
                 const float2 v = pb[pp - u];
                 sacc.x += v.x;
@@ -282,20 +273,33 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
             sacc.x += __shfl_xor_sync(0xffffffffu, sacc.x, sh);
             sacc.y += __shfl_xor_sync(0xffffffffu, sacc.y, sh);
         }
-        if (u == 0 && oseg_active && j >= 0 && j < L + LEAD && kout < bi.out_count) {
-            if (DEMOD) {
-                float ang = fast_arctan2_ref(sacc.y, sacc.x);
-                if (use_override && so == 0 && j == 0) ang = s_misc[0];
-                angrow[j] = ang;
-                ang_prev = ang;
-                have_prev = j >= LEAD;
-                if (a.out_iq && j >= LEAD) a.out_iq[ch * a.out_stride + bi.out_start + kout] = sacc;
-            } else {
-                a.out_iq[ch * a.out_stride + bi.out_start + kout] = sacc;
+        const int j = it * R + ro - (Q - 1);
+        if (ylane && j >= 0 && j < LL) yrow[it * R] = sacc;
+    };
+
+    // ---- epilogue of one finished super-iteration: Q outputs per segment, one thread per output --------
+    auto epilogue = [&](int sup) {
+        if (t >= NSEG * Q) return;
+        const int es = t / Q, er = t - es * Q;
+        const int j = sup * Q + er - (Q - 1);           // 0 = the segment's leading output
+        const int k = k0 + es * L - LEAD + j;           // output index within the block
+        if (j < LEAD || j >= LL || k >= bi.out_count) return;
+        const float2 y = ybuf[es * LL + j];
+        const long long oidx = ch * a.out_stride + bi.out_start + k;
+        if (DEMOD) {
+            const float cur = fast_arctan2_ref(y.y, y.x);
+            float prev;
+            if (use_override && es == 0 && j == 1) prev = s_misc[0];
+            else {
+                const float2 yp = ybuf[es * LL + j - 1];
+                prev = fast_arctan2_ref(yp.y, yp.x);
             }
+            a.audio[oidx] = fm_step_ref(cur, prev, a.phasor_speed);
+            if (bi.out_start + k == a.part.total_out - 1) a.demod_out[ch] = cur;
+            if (a.out_iq) a.out_iq[oidx] = y;
+        } else {
+            a.out_iq[oidx] = y;
         }
-        j += R;
-        kout += R;
     };
 
     // ---- main loop: nsup super-iterations of Q rows (= NS stages, one ring slot each) ----------------
@@ -312,14 +316,11 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
         const uint32_t parity = (uint32_t)(sup & 1);
 #pragma unroll
         for (int i = 0; i < Q; i++) {
-            constexpr int dummy = 0;
-            (void)dummy;
             const int slot = i / R;                 // compile-time after unrolling
             const int par = (sup * NS + slot) & 1;  // partial-buffer parity of this stage
             if (i % R == 0) mbar_wait(&mbar[slot], parity);
             if (seg_active) {
-                const float4 v = *reinterpret_cast<const float4*>(
-                    reinterpret_cast<const unsigned char*>(xme + (i % R) * row4) + slot * stage_bytes);
+                const float4 v = *reinterpret_cast<const float4*>(xme + slot * stage_bytes + (i % R) * row_bytes);
                 float2 RE, IM;
                 if (ROT) {
                     // x' = x * p for both columns; results land directly in the packed (col r, col r+1) pairs
@@ -347,24 +348,20 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
                     }
                 }
                 const int e = (i + 1) % Q;  // the output whose last tap (q = Q-1) was just applied
-                *reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(pme + (i % R) * Ppad) + par * pbuf_half) =
+                *reinterpret_cast<float2*>(pme + par * pbuf_half + (i % R) * prow_bytes) =
                     make_float2(accRe[e].x + accRe[e].y, accIm[e].x + accIm[e].y);
             }
             if (i % R == R - 1) {
                 __syncthreads();                       // stage consumed, partials visible
                 issue((sup + 1) * NS + slot, slot);    // refill the slot just drained
-                reduce_stage(par);
+                reduce_stage(sup * NS + slot, par);
+                // all of the previous super-iteration's outputs were parked before this barrier
+                if (slot == 0 && sup > 0) epilogue(sup - 1);
             }
         }
     }
-    if (DEMOD) {
-        __syncthreads();
-        if (u == 0 && have_prev) {
-            const float prev = angrow[j - R - 1];
-            a.audio[ch * a.out_stride + bi.out_start + (kout - R)] = fm_step_ref(ang_prev, prev, a.phasor_speed);
-            if (bi.out_start + (kout - R) == a.part.total_out - 1) a.demod_out[ch] = ang_prev;
-        }
-    }
+    __syncthreads();
+    epilogue(nsup - 1);
 }
 
 // ---- host side -------------------------------------------------------------------------------------
@@ -393,7 +390,7 @@ DecimPlan* decim_plan_create(const float* taps, int T, int D) {
     if (nseg > 13) nseg = 13;
     if (nseg < 1) nseg = 1;
     p->NSEG = nseg;
-    int nt = nseg * p->P > nseg * 24 ? nseg * p->P : nseg * 24;
+    int nt = nseg * p->P > nseg * 24 ? nseg * p->P : nseg * 24;   // 24 >= Q: also enough epilogue threads
     p->NT = ((nt + 31) / 32) * 32;
     if (p->NT < 64) p->NT = 64;
     p->NSUP = 15;
@@ -422,14 +419,14 @@ void decim_plan_destroy(DecimPlan* p) {
     delete p;
 }
 
-template <int Q, int DT, bool ROT, bool DEMOD>
+template <int Q, int DT, int NSEGT, bool ROT, bool DEMOD>
 static int launch_decim_t(const DecimArgs& a, dim3 grid, int NT, size_t smem, cudaStream_t s) {
     if (NT <= 320) {
-        auto kern = decim_kernel<Q, DT, ROT, DEMOD, 320, 2>;
+        auto kern = decim_kernel<Q, DT, NSEGT, ROT, DEMOD, 320, 2>;
         QDSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, NT, smem, s>>>(a);
     } else {
-        auto kern = decim_kernel<Q, DT, ROT, DEMOD, 640, 1>;
+        auto kern = decim_kernel<Q, DT, NSEGT, ROT, DEMOD, 640, 1>;
         QDSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, NT, smem, s>>>(a);
     }
@@ -473,21 +470,21 @@ int launch_decim(DecimPlan* plan, const float2* hist, int H, const float2* in, c
     dim3 grid((part.max_out + per_tile - 1) / per_tile, part.view.nblocks, nch);
     const size_t stage_bytes = (size_t)a.NSEG * a.R * a.D * sizeof(float2);
     const size_t smem = (size_t)a.NSTAGE * stage_bytes + (size_t)2 * a.NSEG * a.R * (a.P | 1) * sizeof(float2) +
-                        (size_t)a.NSEG * (a.L + lead) * sizeof(float) + 16 + a.NSTAGE * 8 + 64;
+                        (size_t)a.NSEG * (a.L + lead) * sizeof(float2) + 16 + a.NSTAGE * 8 + 64;
     if (smem > 227 * 1024) {
         set_last_error("decim: tile does not fit shared memory (%zu bytes)", smem);
         return -1;
     }
     const bool fused = mode == 1;
-    if (plan->Q == 9 && plan->D == 50)
-        return fused ? launch_decim_t<9, 50, true, true>(a, grid, plan->NT, smem, s)
-                     : launch_decim_t<9, 50, false, false>(a, grid, plan->NT, smem, s);
+    if (plan->Q == 9 && plan->D == 50 && plan->NSEG == 12)   // config 2: 2.4 MS/s -> 48 kS/s, 401 taps
+        return fused ? launch_decim_t<9, 50, 12, true, true>(a, grid, plan->NT, smem, s)
+                     : launch_decim_t<9, 50, 12, false, false>(a, grid, plan->NT, smem, s);
     if (plan->Q == 9)
-        return fused ? launch_decim_t<9, 0, true, true>(a, grid, plan->NT, smem, s)
-                     : launch_decim_t<9, 0, false, false>(a, grid, plan->NT, smem, s);
+        return fused ? launch_decim_t<9, 0, 0, true, true>(a, grid, plan->NT, smem, s)
+                     : launch_decim_t<9, 0, 0, false, false>(a, grid, plan->NT, smem, s);
     if (plan->Q == 6)
-        return fused ? launch_decim_t<6, 0, true, true>(a, grid, plan->NT, smem, s)
-                     : launch_decim_t<6, 0, false, false>(a, grid, plan->NT, smem, s);
+        return fused ? launch_decim_t<6, 0, 0, true, true>(a, grid, plan->NT, smem, s)
+                     : launch_decim_t<6, 0, 0, false, false>(a, grid, plan->NT, smem, s);
     set_last_error("decim: unsupported Q=%d", plan->Q);
     return -1;
 }
