@@ -70,14 +70,12 @@ __device__ __forceinline__ float fast_arctan2_ref(float y, float x) {
     const float c2 = 3.0f * QDSP_FL_M_PI / 4.0f;    // FAST_ATAN2_COEF2 (macro-expanded order)
     const float abs_y = fabsf(y);
     if (x == 0.0f && y == 0.0f) return 0.0f;
-    float angle;
-    if (x >= 0.0f) {
-        const float r = __fdiv_rn(__fsub_rn(x, abs_y), __fadd_rn(x, abs_y));
-        angle = __fsub_rn(c1, __fmul_rn(c1, r));
-    } else {
-        const float r = __fdiv_rn(__fadd_rn(x, abs_y), __fsub_rn(abs_y, x));
-        angle = __fsub_rn(c2, __fmul_rn(c1, r));
-    }
+    // branch-free selection of the reference's two cases; the arithmetic per case is unchanged
+    const bool pos = x >= 0.0f;
+    const float num = pos ? __fsub_rn(x, abs_y) : __fadd_rn(x, abs_y);
+    const float den = pos ? __fadd_rn(x, abs_y) : __fsub_rn(abs_y, x);
+    const float r = __fdiv_rn(num, den);
+    const float angle = __fsub_rn(pos ? c1 : c2, __fmul_rn(c1, r));
     return (y < 0.0f) ? -angle : angle;
 }
 // One FloatFMDemod step (src/dsp/demodulator.h:88-92) given current and previous phase.

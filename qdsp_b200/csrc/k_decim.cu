@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
     }
 
     if (t == 0) {
-        for (int s = 0; s < NS; s++) mbar_init(&mbar[s], NSEG);
+        for (int s = 0; s < NS; s++) mbar_init(&mbar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // leading-angle override of the block's very first output (warp 0)
@@ -192,28 +192,43 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
     }
     __syncthreads();
 
-    // ---- producer: one TMA bulk copy per (segment, stage) -------------------------------------------
-    const float2* gsrc = a.in + seg_base;  // only dereferenced for stages in [fast_lo, fast_hi)
+    // ---- producer: warp 0, lane l issues segment l's TMA bulk copy; one mbarrier arrival per stage ----
+    // (edge tiles -- history before sample 0 or the ragged end of the buffer -- also run the guarded fill)
     float2* xseg = X + (size_t)seg * chunk_elems;
+    const int nactive = (bi.out_count - k0 + L - 1) / L < NSEG ? (bi.out_count - k0 + L - 1) / L : NSEG;
+    const long long tile_first = bi.in_start + (long long)(k0 - LEAD) * D - a.T - pad;
+    const long long tile_last = tile_first + (long long)(nactive - 1) * L * D + (long long)nst * chunk_elems;
+    const bool edge_tile = tile_first < 0 || tile_last > a.n_in;
+    const float2* p_gsrc = nullptr;     // producer lane's segment
+    int p_lo = 0, p_hi = 0;
+    unsigned char* p_dst = nullptr;
+    if (t < 32 && t < nactive) {
+        const long long pbase = tile_first + (long long)t * L * D;
+        const long long lo = pbase >= 0 ? 0 : (-pbase + chunk_elems - 1) / chunk_elems;
+        const long long hi = a.n_in - pbase < 0 ? 0 : (a.n_in - pbase) / chunk_elems;
+        p_lo = (int)(lo < nst ? lo : nst);
+        p_hi = (int)(hi < nst ? hi : nst);
+        p_gsrc = a.in + pbase;
+        p_dst = reinterpret_cast<unsigned char*>(X + (size_t)t * chunk_elems);
+    }
     auto issue = [&](int it, int slot) {
-        if (!in_grid) return;
-        const bool fast = it >= fast_lo && it < fast_hi;
-        if (pair == 0) {
-            if (fast) {
-                mbar_arrive_expect_tx(&mbar[slot], chunk_bytes);
-                tma_bulk_g2s(reinterpret_cast<unsigned char*>(xseg) + slot * stage_bytes,
-                             gsrc + (size_t)it * chunk_elems, chunk_bytes, &mbar[slot]);
-            } else {
-                mbar_arrive(&mbar[slot]);
-            }
+        if (t < 32) {
+            const bool fast = it >= p_lo && it < p_hi;
+            const unsigned m = __ballot_sync(0xffffffffu, fast);
+            if (t == 0) mbar_arrive_expect_tx(&mbar[slot], (uint32_t)__popc(m) * chunk_bytes);
+            __syncwarp();
+            if (fast) tma_bulk_g2s(p_dst + slot * stage_bytes, p_gsrc + (size_t)it * chunk_elems, chunk_bytes, &mbar[slot]);
         }
-        if (!fast && it < live_hi) {
-            VStream<float2> xs{a.hist, a.in, a.H};
-            float2* dst = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(xseg) + slot * stage_bytes);
-            const long long start = seg_base + (long long)it * chunk_elems;
-            for (int e = pair; e < chunk_elems; e += P) {
-                const long long i = start + e;
-                dst[e] = (i < a.n_in) ? xs.at(i) : make_float2(0.f, 0.f);
+        if (edge_tile && in_grid) {
+            const bool fast = it >= fast_lo && it < fast_hi;
+            if (!fast && it < live_hi) {
+                VStream<float2> xs{a.hist, a.in, a.H};
+                float2* dst = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(xseg) + slot * stage_bytes);
+                const long long start = seg_base + (long long)it * chunk_elems;
+                for (int e = pair; e < chunk_elems; e += P) {
+                    const long long i = start + e;
+                    dst[e] = (i < a.n_in) ? xs.at(i) : make_float2(0.f, 0.f);
+                }
             }
         }
     };
@@ -262,10 +277,22 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
         float2 sacc = make_float2(0.f, 0.f);
         if (ovalid) {
             const float2* pb = reinterpret_cast<const float2*>(pbr + par * pbuf_half);
-            for (int pp = u; pp < P; pp += 8) {
-                const float2 v = pb[pp - u];
-                sacc.x += v.x;
-                sacc.y += v.y;
+            if (DT) {
+                constexpr int NPP = ((DT ? DT : 2) / 2 + 7) / 8;
+#pragma unroll
+                for (int i8 = 0; i8 < NPP; i8++) {
+                    if (u + 8 * i8 < P) {
+                        const float2 v = pb[8 * i8];
+                        sacc.x += v.x;
+                        sacc.y += v.y;
+                    }
+                }
+            } else {
+                for (int pp = u; pp < P; pp += 8) {
+                    const float2 v = pb[pp - u];
+                    sacc.x += v.x;
+                    sacc.y += v.y;
+                }
             }
         }
 #pragma unroll
@@ -305,8 +332,8 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
     // ---- main loop: nsup super-iterations of Q rows (= NS stages, one ring slot each) ----------------
 #pragma unroll 1
     for (int sup = 0; sup < nsup; sup++) {
-        if (ROT && (sup & 3) == 0 && seg_active) {
-            // exact phasor re-seed (closed form) every 4*Q rows bounds the recurrence's rounding walk
+        if (ROT && (sup & 7) == 0 && seg_active) {
+            // exact phasor re-seed (closed form) every 8*Q rows bounds the recurrence's rounding walk
             const long long i0 = col0 + (long long)sup * Q * D;
             const float2 p0 = phasor_from_turns(nco_ph0 + nco_step * (uint64_t)i0);
             const float2 p1 = phasor_from_turns(nco_ph0 + nco_step * (uint64_t)(i0 + 1));
@@ -315,49 +342,52 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
         }
         const uint32_t parity = (uint32_t)(sup & 1);
 #pragma unroll
-        for (int i = 0; i < Q; i++) {
-            const int slot = i / R;                 // compile-time after unrolling
+        for (int slot = 0; slot < NS; slot++) {
             const int par = (sup * NS + slot) & 1;  // partial-buffer parity of this stage
-            if (i % R == 0) mbar_wait(&mbar[slot], parity);
+            mbar_wait(&mbar[slot], parity);
             if (seg_active) {
-                const float4 v = *reinterpret_cast<const float4*>(xme + slot * stage_bytes + (i % R) * row_bytes);
-                float2 RE, IM;
-                if (ROT) {
-                    // x' = x * p for both columns; results land directly in the packed (col r, col r+1) pairs
-                    RE.x = fmaf(v.x, PR.x, -(v.y * PI.x));
-                    IM.x = fmaf(v.x, PI.x, v.y * PR.x);
-                    RE.y = fmaf(v.z, PR.y, -(v.w * PI.y));
-                    IM.y = fmaf(v.z, PI.y, v.w * PR.y);
-                    // p *= w for both columns in 4 packed ops
-                    const float2 nPR = __ffma2_rn(PI, neg2(wi2), __fmul2_rn(PR, wr2));
-                    PI = __ffma2_rn(PI, wr2, __fmul2_rn(PR, wi2));
-                    PR = nPR;
-                } else {
-                    RE = make_float2(v.x, v.z);
-                    IM = make_float2(v.y, v.w);
-                }
+                const unsigned char* xs_ = xme + slot * stage_bytes;
+                unsigned char* ps_ = pme + par * pbuf_half;
 #pragma unroll
-                for (int q = 0; q < Q; q++) {
-                    const int sl = (i - q + Q) % Q;
-                    if (q == 0) {
-                        accRe[sl] = __fmul2_rn(RE, tp[0]);
-                        accIm[sl] = __fmul2_rn(IM, tp[0]);
+                for (int r = 0; r < R; r++) {
+                    const int i = slot * R + r;     // row within the super-iteration: compile-time
+                    const float4 v = *reinterpret_cast<const float4*>(xs_ + r * row_bytes);
+                    float2 RE, IM;
+                    if (ROT) {
+                        // x' = x * p for both columns; results land directly in the packed (col r, col r+1) pairs
+                        RE.x = fmaf(v.x, PR.x, -(v.y * PI.x));
+                        IM.x = fmaf(v.x, PI.x, v.y * PR.x);
+                        RE.y = fmaf(v.z, PR.y, -(v.w * PI.y));
+                        IM.y = fmaf(v.z, PI.y, v.w * PR.y);
+                        // p *= w for both columns in 4 packed ops
+                        const float2 nPR = __ffma2_rn(PI, neg2(wi2), __fmul2_rn(PR, wr2));
+                        PI = __ffma2_rn(PI, wr2, __fmul2_rn(PR, wi2));
+                        PR = nPR;
                     } else {
-                        accRe[sl] = __ffma2_rn(RE, tp[q], accRe[sl]);
-                        accIm[sl] = __ffma2_rn(IM, tp[q], accIm[sl]);
+                        RE = make_float2(v.x, v.z);
+                        IM = make_float2(v.y, v.w);
                     }
+#pragma unroll
+                    for (int q = 0; q < Q; q++) {
+                        const int sl = (i - q + Q) % Q;
+                        if (q == 0) {
+                            accRe[sl] = __fmul2_rn(RE, tp[0]);
+                            accIm[sl] = __fmul2_rn(IM, tp[0]);
+                        } else {
+                            accRe[sl] = __ffma2_rn(RE, tp[q], accRe[sl]);
+                            accIm[sl] = __ffma2_rn(IM, tp[q], accIm[sl]);
+                        }
+                    }
+                    const int e = (i + 1) % Q;  // the output whose last tap (q = Q-1) was just applied
+                    *reinterpret_cast<float2*>(ps_ + r * prow_bytes) =
+                        make_float2(accRe[e].x + accRe[e].y, accIm[e].x + accIm[e].y);
                 }
-                const int e = (i + 1) % Q;  // the output whose last tap (q = Q-1) was just applied
-                *reinterpret_cast<float2*>(pme + par * pbuf_half + (i % R) * prow_bytes) =
-                    make_float2(accRe[e].x + accRe[e].y, accIm[e].x + accIm[e].y);
             }
-            if (i % R == R - 1) {
-                __syncthreads();                       // stage consumed, partials visible
-                issue((sup + 1) * NS + slot, slot);    // refill the slot just drained
-                reduce_stage(sup * NS + slot, par);
-                // all of the previous super-iteration's outputs were parked before this barrier
-                if (slot == 0 && sup > 0) epilogue(sup - 1);
-            }
+            __syncthreads();                       // stage consumed, partials visible
+            issue((sup + 1) * NS + slot, slot);    // refill the slot just drained
+            reduce_stage(sup * NS + slot, par);
+            // all of the previous super-iteration's outputs were parked before this barrier
+            if (slot == 0 && sup > 0) epilogue(sup - 1);
         }
     }
     __syncthreads();
