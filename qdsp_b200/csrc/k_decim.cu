@@ -416,15 +416,18 @@ DecimPlan* decim_plan_create(const float* taps, int T, int D) {
     p->NSTAGE = p->Q / 3;
     // segments per CTA: ~320 threads (two CTAs per SM with up to 96 registers per thread: no spills); the
     // reduction role needs 8 lanes per output of a stage, i.e. NT >= 24 * NSEG
-    int nseg = 320 / p->P;
+    // measured on B200 (config 2): 128-thread CTAs x 5 per SM beat 320 x 2 (445 vs 374 GS/s): the per-stage
+    // CTA barrier then only couples 4 warps while four other CTAs keep the SM busy
+    int nseg = 128 / p->P >= 1 ? 128 / p->P : 320 / p->P;
     if (nseg > 13) nseg = 13;
+    if (const char* e = getenv("QDSP_DECIM_NSEG")) nseg = atoi(e) < nseg ? atoi(e) : nseg;
     if (nseg < 1) nseg = 1;
     p->NSEG = nseg;
     int nt = nseg * p->P > nseg * 24 ? nseg * p->P : nseg * 24;   // 24 >= Q: also enough epilogue threads
     p->NT = ((nt + 31) / 32) * 32;
     if (p->NT < 64) p->NT = 64;
-    p->NSUP = 15;
-    if (const char* e = getenv("QDSP_DECIM_NSUP")) p->NSUP = atoi(e) > 1 ? atoi(e) : 15;
+    p->NSUP = 29;
+    if (const char* e = getenv("QDSP_DECIM_NSUP")) p->NSUP = atoi(e) > 1 ? atoi(e) : 29;
     std::vector<float2> tab((size_t)2 * p->Q * p->P, make_float2(0.f, 0.f));
     for (int pad = 0; pad < 2; pad++)
         for (int q = 0; q < p->Q; q++)
@@ -451,15 +454,18 @@ void decim_plan_destroy(DecimPlan* p) {
 
 template <int Q, int DT, int NSEGT, bool ROT, bool DEMOD>
 static int launch_decim_t(const DecimArgs& a, dim3 grid, int NT, size_t smem, cudaStream_t s) {
-    if (NT <= 320) {
-        auto kern = decim_kernel<Q, DT, NSEGT, ROT, DEMOD, 320, 2>;
-        QDSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, NT, smem, s>>>(a);
-    } else {
-        auto kern = decim_kernel<Q, DT, NSEGT, ROT, DEMOD, 640, 1>;
-        QDSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, NT, smem, s>>>(a);
+    // launch bounds pick the CTAs/SM that 96 registers per thread allow (640 threads per SM)
+#define QDSP_DECIM_LAUNCH(MAXT, MINB)                                                                          \
+    {                                                                                                          \
+        auto kern = decim_kernel<Q, DT, NSEGT, ROT, DEMOD, MAXT, MINB>;                                        \
+        QDSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+        kern<<<grid, NT, smem, s>>>(a);                                                                        \
     }
+    if (NT <= 128) QDSP_DECIM_LAUNCH(128, 5)
+    else if (NT <= 160) QDSP_DECIM_LAUNCH(160, 4)
+    else if (NT <= 320) QDSP_DECIM_LAUNCH(320, 2)
+    else QDSP_DECIM_LAUNCH(640, 1)
+#undef QDSP_DECIM_LAUNCH
     QDSP_LAUNCH_OK();
     return 0;
 }
@@ -509,6 +515,12 @@ int launch_decim(DecimPlan* plan, const float2* hist, int H, const float2* in, c
     if (plan->Q == 9 && plan->D == 50 && plan->NSEG == 12)   // config 2: 2.4 MS/s -> 48 kS/s, 401 taps
         return fused ? launch_decim_t<9, 50, 12, true, true>(a, grid, plan->NT, smem, s)
                      : launch_decim_t<9, 50, 12, false, false>(a, grid, plan->NT, smem, s);
+    if (plan->Q == 9 && plan->D == 50 && plan->NSEG == 6)
+        return fused ? launch_decim_t<9, 50, 6, true, true>(a, grid, plan->NT, smem, s)
+                     : launch_decim_t<9, 50, 6, false, false>(a, grid, plan->NT, smem, s);
+    if (plan->Q == 9 && plan->D == 50 && plan->NSEG == 5)
+        return fused ? launch_decim_t<9, 50, 5, true, true>(a, grid, plan->NT, smem, s)
+                     : launch_decim_t<9, 50, 5, false, false>(a, grid, plan->NT, smem, s);
     if (plan->Q == 9)
         return fused ? launch_decim_t<9, 0, 0, true, true>(a, grid, plan->NT, smem, s)
                      : launch_decim_t<9, 0, 0, false, false>(a, grid, plan->NT, smem, s);
