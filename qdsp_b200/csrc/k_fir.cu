@@ -1,13 +1,153 @@
-// placeholder until the register-blocked dense FIR lands
+// qdsp_b200/csrc/k_fir.cu — register-blocked dense complex FIR for sm_100a (FIR<complex_t>::run, reference
+// src/dsp/filter.h:51-74): y[n] = sum_j taps[j] * x[n - (T-1) + j], cf32 samples, real taps.
+//
+// FP32-bound (4*T flop per sample), so the kernel is built around the packed FFMA2 pipe:
+//   * samples are staged in shared memory as quads (re[2m], re[2m+1], im[2m], im[2m+1]); taps as pairs
+//     (h[2u], h[2u+1]). One FFMA2 then performs two real MACs of the SAME output,
+//         accRe += (re[2m], re[2m+1]) * (h[2u], h[2u+1])     (lanes summed once at the end)
+//     so no register holds a duplicated tap and every FFMA2 does two useful MACs.
+//   * outputs whose window starts on an odd sample use a second tap table shifted by one
+//     (h[2u-1], h[2u]); a warp works on one parity, so tap loads are warp-uniform broadcasts.
+//   * each thread owns R = 9 outputs (stride 2) and slides a 9-quad register window over the taps:
+//     one 128-bit shared load + one broadcast tap load per 18 FFMA2. R odd makes the lane stride
+//     9*16 B, which is conflict-free for 128-bit shared loads.
+//   * the whole input window of a tile stays resident (NOUT + T - 1 samples), so the tap loop runs
+//     without any block-level barrier; two CTAs per SM overlap one tile's staging with the other's math.
 #include <new>
+#include <vector>
 #include "internal.cuh"
 #include "kernels.cuh"
+
 namespace qdsp {
-struct FirPlan { int T; };
-FirPlan* fir_plan_create(const float*, int) { return nullptr; }
-void fir_plan_destroy(FirPlan* p) { delete p; }
-int launch_fir_dense(FirPlan*, const float2*, int, const float2*, long long, int, float2*, cudaStream_t) {
-    set_last_error("dense FIR kernel not built");
-    return -1;
+
+constexpr int kFirR = 9;                        // outputs per thread
+constexpr int kFirWarps = 8;                    // 4 even-parity + 4 odd-parity warps
+constexpr int kFirThreads = kFirWarps * 32;
+constexpr int kFirNout = (kFirWarps / 2) * 64 * kFirR;   // 2304 outputs per tile
+
+struct FirPlan {
+    int T = 0;
+    int U = 0;                  // tap pairs per parity table, multiple of kFirR
+    float2* taps_dev = nullptr; // [2][U]: even table (h[2u], h[2u+1]); odd table (h[2u-1], h[2u])
+};
+
+FirPlan* fir_plan_create(const float* taps, int T) {
+    if (T < 2) return nullptr;
+    FirPlan* p = new (std::nothrow) FirPlan();
+    if (!p) return nullptr;
+    p->T = T;
+    int U = (T + 2) / 2;                        // enough pairs for the odd table's extra leading zero
+    U = ((U + kFirR - 1) / kFirR) * kFirR;
+    p->U = U;
+    // shared memory: quads for NOUT/2 + U pairs (+ slack) and both tap tables
+    const size_t smem = ((size_t)kFirNout / 2 + U + 8) * 16 + (size_t)2 * U * 8;
+    if (smem > 110 * 1024) {                    // keep two CTAs per SM; longer filters use the generic kernel
+        delete p;
+        return nullptr;
+    }
+    std::vector<float2> tab((size_t)2 * U, make_float2(0.f, 0.f));
+    auto h = [&](int j) { return (j >= 0 && j < T) ? taps[j] : 0.0f; };
+    for (int u = 0; u < U; u++) {
+        tab[u] = make_float2(h(2 * u), h(2 * u + 1));
+        tab[(size_t)U + u] = make_float2(h(2 * u - 1), h(2 * u));
+    }
+    if (cudaMalloc(&p->taps_dev, tab.size() * sizeof(float2)) != cudaSuccess ||
+        cudaMemcpy(p->taps_dev, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_last_error("fir_plan_create: tap upload failed");
+        delete p;
+        return nullptr;
+    }
+    return p;
 }
+void fir_plan_destroy(FirPlan* p) {
+    if (!p) return;
+    if (p->taps_dev) cudaFree(p->taps_dev);
+    delete p;
+}
+
+__global__ void __launch_bounds__(kFirThreads, 2)
+fir_dense_kernel(VStream<float2> xs, long long count, const float2* __restrict__ taps, int T, int U,
+                 float2* __restrict__ out) {
+    constexpr int R = kFirR;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int npairs = kFirNout / 2 + U + 8;
+    float4* sq = reinterpret_cast<float4*>(smem_raw);                 // [npairs] sample quads
+    float2* st = reinterpret_cast<float2*>(smem_raw + (size_t)npairs * 16);  // [2][U] tap pairs
+    const int t = threadIdx.x;
+    const long long n_t = (long long)blockIdx.x * kFirNout;           // first output of the tile
+    const long long B = n_t - (T - 1);                                // sample index of quad 0, element 0
+
+    // ---- staging: taps, then the tile's window as (re, re, im, im) quads --------------------------
+    for (int i = t; i < 2 * U; i += kFirThreads) st[i] = taps[i];
+    {
+        float* sf = reinterpret_cast<float*>(sq);
+        const int nsamp = 2 * npairs;
+        for (int e = t; e < nsamp; e += kFirThreads) {
+            const long long i = B + e;
+            const float2 v = (i < count) ? xs.at(i) : make_float2(0.f, 0.f);
+            const int q = e >> 1, h = e & 1;
+            sf[4 * q + h] = v.x;
+            sf[4 * q + 2 + h] = v.y;
+        }
+    }
+    __syncthreads();
+
+    // ---- roles: warp w: parity = w & 1, warp-pair wp = w >> 1 covers 64*R consecutive outputs ----------
+    const int w = t >> 5, lane = t & 31;
+    const int parity = w & 1, wp = w >> 1;
+    const int j0 = wp * 32 * R + lane * R;        // first pair index of this thread's window (u = 0)
+    const float2* tt = st + parity * U;
+    const float4* win = sq + j0;
+
+    float2 accRe[R], accIm[R];
+    float4 W[R];
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+        accRe[i] = make_float2(0.f, 0.f);
+        accIm[i] = make_float2(0.f, 0.f);
+        W[i] = win[i];
+    }
+    // output i accumulates H_u (.) S_{j0 + i + u}; window register W[(u + i) % R] holds S_{j0 + i + u}
+#pragma unroll 1
+    for (int u0 = 0; u0 < U; u0 += R) {
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+            const float2 hh = tt[u0 + k];
+#pragma unroll
+            for (int i = 0; i < R; i++) {
+                const float4 s = W[(k + i) % R];
+                accRe[i] = __ffma2_rn(make_float2(s.x, s.y), hh, accRe[i]);
+                accIm[i] = __ffma2_rn(make_float2(s.z, s.w), hh, accIm[i]);
+            }
+            W[k] = win[u0 + k + R];               // S_{j0 + (u0+k+1) + (R-1)} replaces S_{j0 + u0 + k}
+        }
+    }
+    // ---- store: outputs n = n_t + 2*(j0 + i) + parity ------------------------------------------------
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+        const long long n = n_t + 2 * (long long)(j0 + i) + parity;
+        if (n < count) out[n] = make_float2(accRe[i].x + accRe[i].y, accIm[i].x + accIm[i].y);
+    }
+}
+
+int launch_fir_dense(FirPlan* plan, const float2* hist, int H, const float2* in, long long count, int lead,
+                     float2* out, cudaStream_t s) {
+    if (count <= 0) return 0;
+    if (lead != 1) {
+        set_last_error("fir_dense: only the FIR alignment (lead = 1) is implemented");
+        return -1;
+    }
+    VStream<float2> xs{hist, in, H};
+    const size_t smem = ((size_t)kFirNout / 2 + plan->U + 8) * 16 + (size_t)2 * plan->U * 8;
+    static bool attr_set = false;
+    if (!attr_set) {
+        QDSP_CUDA_OK(cudaFuncSetAttribute(fir_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        attr_set = true;
+    }
+    const long long tiles = (count + kFirNout - 1) / kFirNout;
+    fir_dense_kernel<<<(unsigned)tiles, kFirThreads, smem, s>>>(xs, count, plan->taps_dev, plan->T, plan->U, out);
+    QDSP_LAUNCH_OK();
+    return 0;
+}
+
 }  // namespace qdsp

@@ -244,3 +244,33 @@ def test_costas_chunked_scan(order, gen):
     assert np.abs(y - yo).max() <= 1e-4, np.abs(y - yo).max()
     stg = pl.get_state()
     assert abs(stg[0] - st[0]) <= 1e-5
+
+
+@pytest.mark.parametrize("variant", [1, 0])
+def test_long_fir_4095_taps(variant):
+    # config 3's filter (BlackmanWindow(100e3, 4*fs/4095, fs) -> 4095 taps) on a short stream, fed in
+    # uneven run() blocks; compared with the oracle restatement past the uninitialised-history prefix
+    from qdsp_b200 import blocks as B, synth
+
+    P = loader.port()
+    taps = P.blackman_taps(100e3, 4 * 2.4e6 / 4095, 2.4e6)
+    assert len(taps) == 4095
+    x = synth.uniform_cf32(3, 0, 30000)
+    f = B.FIR(B.BlackmanWindow(100e3, 4 * 2.4e6 / 4095, 2.4e6))
+    f.set_variant(variant)
+    y = np.concatenate([f.process(x[:7001]), f.process(x[7001:7002]), f.process(x[7002:])])
+    yo = P.fir_cf32(taps, x)
+    assert rel_l2(y, yo) <= IQ_TOL, rel_l2(y, yo)
+
+
+def test_dense_fir_even_tap_count_and_tiny_inputs():
+    from qdsp_b200 import blocks as B, synth
+
+    P = loader.port()
+    for T in (2, 64, 126, 1000):
+        taps = (synth.uniform_f32(40 + T, 0, T) / T).astype(np.float32)
+        x = synth.uniform_cf32(41, 0, 5000)
+        f = B.FIR(B._TapsWindow(taps))
+        y = np.concatenate([f.process(x[:1]), f.process(x[1:3]), f.process(x[3:])])
+        yo = P.fir_cf32(taps, x)
+        assert rel_l2(y, yo) <= IQ_TOL, (T, rel_l2(y, yo))
