@@ -1,0 +1,87 @@
+// include/dsp/demodulator.h — FloatFMDemod and FMDemod (reference src/dsp/demodulator.h:33-187). The kernel
+// evaluates the reference's fast_arctan2 phase-difference formula with its exact float sequence (not an
+// atan2 of a conjugate product: SURVEY.md Q6). AM/SSB/stereo/MSK/PSK demodulators are outside the hot path.
+#pragma once
+#include <dsp/block.h>
+
+namespace dsp {
+    namespace detail {
+        template <class SELF, class OUT_T, int STEREO>
+        class fm_demod_base : public generic_block<SELF> {
+            using base = generic_block<SELF>;
+
+        public:
+            ~fm_demod_base() {
+                base::stop();
+                if (h) { qdsp_fmdemod_destroy(h); }
+            }
+            void init(stream<complex_t>* in, float sampleRate, float deviation) {
+                _in = in;
+                _sampleRate = sampleRate;
+                _deviation = deviation;
+                rebuild();
+                base::registerInput(_in);
+                base::registerOutput(&out);
+            }
+            void setInput(stream<complex_t>* in) {
+                std::lock_guard<std::mutex> lck(base::ctrlMtx);
+                base::tempStop();
+                base::unregisterInput(_in);
+                _in = in;
+                base::registerInput(_in);
+                base::tempStart();
+            }
+            void setSampleRate(float sampleRate) {
+                std::lock_guard<std::mutex> lck(base::ctrlMtx);
+                base::tempStop();
+                _sampleRate = sampleRate;
+                rebuild();
+                base::tempStart();
+            }
+            float getSampleRate() { return _sampleRate; }
+            void setDeviation(float deviation) {
+                std::lock_guard<std::mutex> lck(base::ctrlMtx);
+                base::tempStop();
+                _deviation = deviation;
+                rebuild();
+                base::tempStart();
+            }
+            float getDeviation() { return _deviation; }
+            int run() override {
+                const int count = _in->readDevice(base::cuStream);
+                if (count < 0) { return -1; }
+                out.acquireWriteDev(base::cuStream);
+                const long long n = qdsp_fmdemod_process(h, _in->readDev(), out.writeDev(), count, base::cuStream);
+                _in->flushDevice(base::cuStream);
+                if (n < 0) { return -1; }
+                if (!out.swapDevice(count, base::cuStream)) { return -1; }
+                return count;
+            }
+
+            stream<OUT_T> out;
+
+        private:
+            void rebuild() {
+                float phase = 0.0f;
+                if (h) { phase = qdsp_fmdemod_get_phase(h); qdsp_fmdemod_destroy(h); }
+                h = qdsp_fmdemod_create(_sampleRate, _deviation, STEREO);
+                qdsp_fmdemod_set_phase(h, phase);
+            }
+            float _sampleRate = 1, _deviation = 1;
+            stream<complex_t>* _in = nullptr;
+            qdsp_fmdemod* h = nullptr;
+        };
+    }
+
+    class FloatFMDemod : public detail::fm_demod_base<FloatFMDemod, float, 0> {
+    public:
+        FloatFMDemod() {}
+        FloatFMDemod(stream<complex_t>* in, float sampleRate, float deviation) { init(in, sampleRate, deviation); }
+    };
+
+    class FMDemod : public detail::fm_demod_base<FMDemod, stereo_t, 1> {
+    public:
+        FMDemod() {}
+        FMDemod(stream<complex_t>* in, float sampleRate, float deviation) { init(in, sampleRate, deviation); }
+    };
+}

@@ -51,6 +51,12 @@ int qdsp_enable_peer_access(int device, int peer);
 qdsp_stream_t qdsp_stream_create(void);
 void qdsp_stream_destroy(qdsp_stream_t s);
 int qdsp_stream_sync(qdsp_stream_t s);
+/* events order work between the per-block CUDA streams of the dsp:: mirror (include/dsp/stream.h) */
+void* qdsp_event_create(void);
+void qdsp_event_destroy(void* ev);
+int qdsp_event_record(void* ev, qdsp_stream_t s);
+int qdsp_stream_wait_event(qdsp_stream_t s, void* ev);
+int qdsp_event_sync(void* ev);
 /* number of kernels this library has launched in this process (bench.py "gpu_launches") */
 long long qdsp_launch_count(void);
 

@@ -282,6 +282,30 @@ int qdsp_stream_sync(qdsp_stream_t s) {
     return 0;
 }
 
+void* qdsp_event_create(void) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
+        set_last_error("cudaEventCreate failed");
+        return nullptr;
+    }
+    return (void*)e;
+}
+void qdsp_event_destroy(void* ev) {
+    if (ev) cudaEventDestroy((cudaEvent_t)ev);
+}
+int qdsp_event_record(void* ev, qdsp_stream_t s) {
+    QDSP_CUDA_OK(cudaEventRecord((cudaEvent_t)ev, as_stream(s)));
+    return 0;
+}
+int qdsp_stream_wait_event(qdsp_stream_t s, void* ev) {
+    QDSP_CUDA_OK(cudaStreamWaitEvent(as_stream(s), (cudaEvent_t)ev, 0));
+    return 0;
+}
+int qdsp_event_sync(void* ev) {
+    QDSP_CUDA_OK(cudaEventSynchronize((cudaEvent_t)ev));
+    return 0;
+}
+
 // =================================================================================================
 // C ABI: tap design (host). Float expression order follows the reference so the taps are
 // bit-identical; this file is compiled for baseline x86-64 (no FMA contraction on the host).

@@ -42,6 +42,11 @@ SIGNATURES = {
     "qdsp_stream_destroy": (None, [_vp]),
     "qdsp_stream_sync": (_i, [_vp]),
     "qdsp_launch_count": (_ll, []),
+    "qdsp_event_create": (_vp, []),
+    "qdsp_event_destroy": (None, [_vp]),
+    "qdsp_event_record": (_i, [_vp, _vp]),
+    "qdsp_stream_wait_event": (_i, [_vp, _vp]),
+    "qdsp_event_sync": (_i, [_vp]),
     "qdsp_blackman_tap_count": (_i, [_f, _f, _f]),
     "qdsp_blackman_taps": (None, [_f, _f, _f, _fp, _i, _f]),
     "qdsp_blackman_bandpass_taps": (None, [_f, _f, _f, _f, _fp, _i, _f]),
