@@ -139,6 +139,10 @@ qdsp_vfofm* qdsp_vfofm_create(float offset, float inSampleRate, float outSampleR
 void qdsp_vfofm_destroy(qdsp_vfofm* h);
 int qdsp_vfofm_design(qdsp_vfofm* h, int* tapCount, int* interp, int* decim);
 int qdsp_vfofm_set_offset(qdsp_vfofm* h, float offset);                    /* VFO::setOffset, vfo.h:87-90 */
+/* NCO phase at the current stream position, as VOLK's `lv_32fc_t* phase` (processing.h:64,78): lets a caller
+ * (or a parity test) re-synchronise the closed-form oscillator with a recursive float32 reference phasor */
+void qdsp_vfofm_get_phase(qdsp_vfofm* h, float* re, float* im);
+int qdsp_vfofm_set_phase(qdsp_vfofm* h, float re, float im);
 long long qdsp_vfofm_out_count(qdsp_vfofm* h, long long count, const int* blocks, int nblocks, int block_size);
 long long qdsp_vfofm_process(qdsp_vfofm* h, const void* in_dev, float* audio_out_dev, void* iq_out_dev,
                              long long count, const int* blocks, int nblocks, int block_size, int* out_counts,

@@ -475,6 +475,14 @@ class VFOFM(_Block):
     def set_variant(self, v: int):
         _L().qdsp_vfofm_set_variant(self.h, v)
 
+    def get_phase(self) -> complex:
+        re, im = C.c_float(), C.c_float()
+        _L().qdsp_vfofm_get_phase(self.h, C.byref(re), C.byref(im))
+        return complex(re.value, im.value)
+
+    def set_phase(self, p: complex):
+        check(_L().qdsp_vfofm_set_phase(self.h, float(p.real), float(p.imag)))
+
     def reset(self):
         check(_L().qdsp_vfofm_reset(self.h))
 

@@ -551,6 +551,17 @@ int qdsp_vfofm_set_offset(qdsp_vfofm* h, float offset) {
     n.phase = cur_phase - n.step * (uint64_t)h->c.abs_pos;
     return h->c.upload_nco();
 }
+void qdsp_vfofm_get_phase(qdsp_vfofm* h, float* re, float* im) {
+    Nco n = h->c.nco[0];
+    n.phase = n.phase + n.step * (uint64_t)h->c.abs_pos;
+    n.get_phase(re, im);
+}
+int qdsp_vfofm_set_phase(qdsp_vfofm* h, float re, float im) {
+    Nco& n = h->c.nco[0];
+    n.set_phase(re, im);                              // phase at the current position ...
+    n.phase -= n.step * (uint64_t)h->c.abs_pos;       // ... expressed as the constant of the closed form
+    return h->c.upload_nco();
+}
 long long qdsp_vfofm_out_count(qdsp_vfofm* h, long long count, const int* blocks, int nblocks, int block_size) {
     Partition p;
     if (p.build(count, blocks, nblocks, block_size, h->c.interp, h->c.decim, nullptr) != 0) return -1;

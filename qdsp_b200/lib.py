@@ -93,6 +93,8 @@ SIGNATURES = {
     "qdsp_vfofm_destroy": (None, [_vp]),
     "qdsp_vfofm_design": (_i, [_vp, _ip, _ip, _ip]),
     "qdsp_vfofm_set_offset": (_i, [_vp, _f]),
+    "qdsp_vfofm_get_phase": (None, [_vp, _fp, _fp]),
+    "qdsp_vfofm_set_phase": (_i, [_vp, _f, _f]),
     "qdsp_vfofm_out_count": (_ll, [_vp, _ll, _ip, _i, _i]),
     "qdsp_vfofm_process": (_ll, [_vp, _vp, _vp, _vp, _ll, _ip, _i, _i, _ip, _vp]),
     "qdsp_vfofm_process_host": (_ll, [_vp, _vp, _vp, _ll, _i, _vp]),

@@ -85,6 +85,10 @@ def test_cpp_graph_matches_oracle(qlib, tmp_path, mode):
     args = [EXE, str(fin), str(fout), str(blk)] + (["fused"] if mode == "fused" else [])
     subprocess.check_call(args, timeout=120)
     y = np.fromfile(fout, np.float32)
-    ref, _ = loader.port().vfo_fm(250e3, 2.4e6, 48e3, 48e3, 5e3, x, blk)
+    # full length vs the reference chain with the drift-free rotator; first 2 blocks vs the float32 rotator
+    # (its phase drift reaches the audio through fast_arctan2 after ~2e5 samples: DESIGN.md "NCO")
+    ref, _ = loader.port().vfo_fm(250e3, 2.4e6, 48e3, 48e3, 5e3, x, blk, nco_f64=True)
     assert y.shape == ref.shape
     assert np.abs(y[16:] - ref[16:]).max() <= 1e-4
+    ref32, _ = loader.port().vfo_fm(250e3, 2.4e6, 48e3, 48e3, 5e3, x[:2 * blk], blk)
+    assert np.abs(y[16:len(ref32)] - ref32[16:]).max() <= 1e-4

@@ -274,3 +274,36 @@ def test_dense_fir_even_tap_count_and_tiny_inputs():
         y = np.concatenate([f.process(x[:1]), f.process(x[1:3]), f.process(x[3:])])
         yo = P.fir_cf32(taps, x)
         assert rel_l2(y, yo) <= IQ_TOL, (T, rel_l2(y, yo))
+
+
+def test_long_stream_audio_nco_attribution():
+    # 2^21 samples through the fused chain.
+    # (a) vs the reference chain with the drift-free (float64) rotator: <= 1e-4 everywhere;
+    # (b) vs the recursive float32 rotator the un-synchronised comparison does NOT hold: after ~2e5 samples that
+    #     rotator locks onto an exactly periodic orbit whose rate differs from arg(phaseDelta) by 1.35e-8
+    #     rad/sample, and the accumulated offset reaches the audio through fast_arctan2's nonlinearity;
+    # (c) with the rotator's phase handed over at every run() call (VOLK's `lv_32fc_t* phase` in/out, here
+    #     qdsp_vfofm_set_phase) parity with the float32 reference holds over the whole stream.
+    from qdsp_b200 import blocks as B, synth
+
+    P = loader.port()
+    n, blk = 1 << 21, 4000
+    x = synth.cfg2_input(0, n)
+    y = B.VFOFM(250e3, 2.4e6, 48e3, 48e3, 5e3).process(x, blk)
+    a64, oc64 = P.vfo_fm(250e3, 2.4e6, 48e3, 48e3, 5e3, x, blk, nco_f64=True)
+    assert y.shape == a64.shape
+    assert np.abs(y[16:] - a64[16:]).max() <= AUDIO_TOL
+    a32, _ = P.vfo_fm(250e3, 2.4e6, 48e3, 48e3, 5e3, x, blk)
+    assert np.abs(y[16:] - a32[16:]).max() > AUDIO_TOL
+    inc = P.xlator_phase_delta(2.4e6, -250e3)
+    v = B.VFOFM(250e3, 2.4e6, 48e3, 48e3, 5e3)
+    phase = 1 + 0j
+    outs = []
+    for b0 in range(0, n, blk):
+        seg = x[b0:b0 + blk]
+        v.set_phase(phase)
+        outs.append(v.process(seg, blk))
+        _, phase = P.rotator(seg, inc, phase, blk)   # the reference's phasor state after this run() call
+    yi = np.concatenate(outs)
+    assert yi.shape == a32.shape
+    assert np.abs(yi[16:] - a32[16:]).max() <= AUDIO_TOL, np.abs(yi[16:] - a32[16:]).max()
