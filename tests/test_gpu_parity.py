@@ -287,7 +287,7 @@ def test_long_stream_audio_nco_attribution():
     from qdsp_b200 import blocks as B, synth
 
     P = loader.port()
-    n, blk = 1 << 21, 4000
+    n, blk = 1 << 21, 2000
     x = synth.cfg2_input(0, n)
     y = B.VFOFM(250e3, 2.4e6, 48e3, 48e3, 5e3).process(x, blk)
     a64, oc64 = P.vfo_fm(250e3, 2.4e6, 48e3, 48e3, 5e3, x, blk, nco_f64=True)
