@@ -134,6 +134,9 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
     float2* ybuf = reinterpret_cast<float2*>(smem_raw + NS * stage_bytes + 2 * pbuf_half);   // [NSEG][LL]
     uint64_t* mbar = reinterpret_cast<uint64_t*>(ybuf + NSEG * LL);                          // [NS]
     float* s_misc = reinterpret_cast<float*>(mbar + NS);                                     // [0]=override angle
+    // wide rows (more than 64 column pairs): the partial reduce runs in two levels, P -> 64 -> 1
+    const bool two_level = (DT == 0) && P > 64;
+    float2* P2 = reinterpret_cast<float2*>(s_misc + 4);                                      // [2][NSEG*R][64]
 
     // ---- thread roles ------------------------------------------------------------------------
     const int seg = t / P;
@@ -273,7 +276,47 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
     for (int s = 0; s < NS; s++) issue(s, s);
     __syncthreads();
 
+    // level 2 of the wide-row reduce (also the whole reduce of narrow rows): 8 lanes per output
+    auto finish_output = [&](int it, float2 sacc) {
+#pragma unroll
+        for (int sh = 4; sh > 0; sh >>= 1) {
+            sacc.x += __shfl_xor_sync(0xffffffffu, sacc.x, sh);
+            sacc.y += __shfl_xor_sync(0xffffffffu, sacc.y, sh);
+        }
+        const int j = it * R + ro - (Q - 1);
+        if (ylane && j >= 0 && j < LL) yrow[it * R] = sacc;
+    };
     auto reduce_stage = [&](int it, int par) {
+        if (two_level) {
+            // level 1, stage `it`: 64 lanes per output fold P partials into 64
+            const int NO = NSEG * R;
+            for (int idx = t; idx < NO * 64; idx += blockDim.x) {
+                const int o1 = idx >> 6, l1 = idx & 63;
+                const float2* pb = reinterpret_cast<const float2*>(reinterpret_cast<const unsigned char*>(Pbuf) + par * pbuf_half) + o1 * Ppad;
+                float2 s1 = make_float2(0.f, 0.f);
+                for (int pp = l1; pp < P; pp += 64) {
+                    const float2 v = pb[pp];
+                    s1.x += v.x;
+                    s1.y += v.y;
+                }
+                P2[(par * NO + o1) * 64 + l1] = s1;
+            }
+            // level 2, stage `it - 1` (its level-1 sums became visible at this stage's barrier)
+            if (it >= 1) {
+                float2 sacc = make_float2(0.f, 0.f);
+                if (ovalid) {
+                    const float2* p2 = P2 + (((par ^ 1) * NO + o) * 64);
+#pragma unroll
+                    for (int i8 = 0; i8 < 8; i8++) {
+                        const float2 v = p2[u + 8 * i8];
+                        sacc.x += v.x;
+                        sacc.y += v.y;
+                    }
+                }
+                finish_output(it - 1, sacc);
+            }
+            return;
+        }
         float2 sacc = make_float2(0.f, 0.f);
         if (ovalid) {
             const float2* pb = reinterpret_cast<const float2*>(pbr + par * pbuf_half);
@@ -295,13 +338,7 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
                 }
             }
         }
-#pragma unroll
-        for (int sh = 4; sh > 0; sh >>= 1) {
-            sacc.x += __shfl_xor_sync(0xffffffffu, sacc.x, sh);
-            sacc.y += __shfl_xor_sync(0xffffffffu, sacc.y, sh);
-        }
-        const int j = it * R + ro - (Q - 1);
-        if (ylane && j >= 0 && j < LL) yrow[it * R] = sacc;
+        finish_output(it, sacc);
     };
 
     // ---- epilogue of one finished super-iteration: Q outputs per segment, one thread per output --------
@@ -391,6 +428,22 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
         }
     }
     __syncthreads();
+    if (two_level) {
+        // flush level 2 of the last stage
+        float2 sacc = make_float2(0.f, 0.f);
+        const int lastit = nsup * NS - 1, NO = NSEG * R;
+        if (ovalid) {
+            const float2* p2 = P2 + (((lastit & 1) * NO + o) * 64);
+#pragma unroll
+            for (int i8 = 0; i8 < 8; i8++) {
+                const float2 v = p2[u + 8 * i8];
+                sacc.x += v.x;
+                sacc.y += v.y;
+            }
+        }
+        finish_output(lastit, sacc);
+        __syncthreads();
+    }
     epilogue(nsup - 1);
 }
 
@@ -506,7 +559,8 @@ int launch_decim(DecimPlan* plan, const float2* hist, int H, const float2* in, c
     dim3 grid((part.max_out + per_tile - 1) / per_tile, part.view.nblocks, nch);
     const size_t stage_bytes = (size_t)a.NSEG * a.R * a.D * sizeof(float2);
     const size_t smem = (size_t)a.NSTAGE * stage_bytes + (size_t)2 * a.NSEG * a.R * (a.P | 1) * sizeof(float2) +
-                        (size_t)a.NSEG * (a.L + lead) * sizeof(float2) + 16 + a.NSTAGE * 8 + 64;
+                        (size_t)a.NSEG * (a.L + lead) * sizeof(float2) + 16 + a.NSTAGE * 8 + 64 +
+                        (a.P > 64 ? (size_t)2 * a.NSEG * a.R * 64 * sizeof(float2) : 0);
     if (smem > 227 * 1024) {
         set_last_error("decim: tile does not fit shared memory (%zu bytes)", smem);
         return -1;

@@ -307,3 +307,23 @@ def test_long_stream_audio_nco_attribution():
     yi = np.concatenate(outs)
     assert yi.shape == a32.shape
     assert np.abs(yi[16:] - a32[16:]).max() <= AUDIO_TOL, np.abs(yi[16:] - a32[16:]).max()
+
+
+@pytest.mark.parametrize("variant", [1, 0])
+def test_channelizer_config4_geometry(variant):
+    # config 4's real geometry (61.44 MS/s -> 48 kS/s: 10241 taps, I=1, D=1280: 640 column pairs per row,
+    # two-level partial reduce), 3 channels, vs the oracle with the drift-free rotator and vs the float one
+    from qdsp_b200 import blocks as B, synth
+
+    P = loader.port()
+    n, blk = 1 << 18, 81920
+    x = synth.cfg4_input(0, n, nch=256)
+    offs = [-30.6e6, 120e3, 17.88e6]  # carriers k = 0, 128, 202 of the synthetic wideband stream
+    ch = B.Channelizer(offs, 61.44e6, 48e3, 48e3, 5e3)
+    assert (ch.tapCount, ch._interp, ch._decim) == (10241, 1, 1280)
+    ch.set_variant(variant)
+    y = ch.process(x, blk)
+    for c, off in enumerate(offs):
+        a64, _ = P.vfo_fm(off, 61.44e6, 48e3, 48e3, 5e3, x, blk, nco_f64=True)
+        assert y[c].shape == a64.shape
+        assert np.abs(y[c][16:] - a64[16:]).max() <= AUDIO_TOL, (c, np.abs(y[c][16:] - a64[16:]).max())
