@@ -106,7 +106,7 @@ __device__ float2 direct_output_warp(const DecimArgs& a, long long win_start, ui
 // packed f32x2 helpers for the two-column phasor recurrence
 __device__ __forceinline__ float2 neg2(float2 v) { return make_float2(-v.x, -v.y); }
 
-template <int Q, int DT, int NSEGT, bool ROT, bool DEMOD, int MAXT, int MINB>
+template <int Q, int DT, int NSEGT, bool ROT, bool DEMOD, bool SUPRED, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
     constexpr int R = 3;            // rows per stage per segment
     constexpr int NS = Q / R;       // stages per super-iteration == ring depth: slot index is static
@@ -127,8 +127,13 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
     const uint32_t chunk_bytes = (uint32_t)chunk_elems * 8u;
     const uint32_t stage_bytes = (uint32_t)NSEG * chunk_bytes;
     const int Ppad = P | 1;
-    const uint32_t pbuf_half = (uint32_t)(NSEG * R * Ppad) * 8u;     // one parity of the partial buffer
-    const int LL = L + LEAD;                                         // outputs kept per segment
+    // SUPRED (narrow rows): partials of a whole super-iteration (Q rows) are kept and reduced once per
+    // super-iteration by 2 lanes per output; otherwise per stage (R rows) by 8 lanes per output
+    constexpr int PROWS = SUPRED ? Q : R;
+    const uint32_t pbuf_half = (uint32_t)(NSEG * PROWS * Ppad) * 8u; // one parity of the partial buffer
+    constexpr int RY = 4 * Q;                                        // SUPRED: parked outputs live in a ring
+    const int LL = SUPRED ? RY : L + LEAD;                           // outputs kept per segment
+    const int LOUT = L + LEAD;                                       // outputs produced per segment
     float2* X = reinterpret_cast<float2*>(smem_raw);
     float2* Pbuf = reinterpret_cast<float2*>(smem_raw + NS * stage_bytes);                   // [2][NSEG*R][Ppad]
     float2* ybuf = reinterpret_cast<float2*>(smem_raw + NS * stage_bytes + 2 * pbuf_half);   // [NSEG][LL]
@@ -261,7 +266,7 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
 
     // my float4 (two adjacent samples) in slot 0, row 0; my partial slot in parity 0, row 0
     const unsigned char* xme = reinterpret_cast<const unsigned char*>(reinterpret_cast<const float4*>(xseg) + pair);
-    unsigned char* pme = reinterpret_cast<unsigned char*>(Pbuf + (seg * R) * Ppad + pair);
+    unsigned char* pme = reinterpret_cast<unsigned char*>(Pbuf + (seg * PROWS) * Ppad + pair);
     const uint32_t row_bytes = (uint32_t)D * 8u;
     const uint32_t prow_bytes = (uint32_t)Ppad * 8u;
 
@@ -284,7 +289,7 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
             sacc.y += __shfl_xor_sync(0xffffffffu, sacc.y, sh);
         }
         const int j = it * R + ro - (Q - 1);
-        if (ylane && j >= 0 && j < LL) yrow[it * R] = sacc;
+        if (ylane && j >= 0 && j < LOUT) yrow[it * R] = sacc;
     };
     auto reduce_stage = [&](int it, int par) {
         if (two_level) {
@@ -341,21 +346,44 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
         finish_output(it, sacc);
     };
 
+    // SUPRED: all NSEG*Q outputs of super-iteration `sup`, 2 lanes per output (packed adds), parked in the ring
+    auto reduce_super = [&](int sup) {
+        const int o2 = t >> 1, u2 = t & 1;
+        float2 sacc = make_float2(0.f, 0.f);
+        const bool v2 = o2 < NSEG * Q;
+        const int s2 = o2 / Q, i2 = o2 - s2 * Q;
+        if (v2) {
+            const float2* pb = reinterpret_cast<const float2*>(reinterpret_cast<const unsigned char*>(Pbuf) + (sup & 1) * pbuf_half) + o2 * Ppad;
+            if (DT) {
+                constexpr int NP2 = ((DT ? DT : 2) / 2 + 1) / 2;
+#pragma unroll
+                for (int i = 0; i < NP2; i++)
+                    if (u2 + 2 * i < P) sacc = __fadd2_rn(sacc, pb[u2 + 2 * i]);
+            } else {
+                for (int pp = u2; pp < P; pp += 2) sacc = __fadd2_rn(sacc, pb[pp]);
+            }
+        }
+        sacc.x += __shfl_xor_sync(0xffffffffu, sacc.x, 1);
+        sacc.y += __shfl_xor_sync(0xffffffffu, sacc.y, 1);
+        const int j = sup * Q + i2 - (Q - 1);
+        if (v2 && u2 == 0 && j >= 0 && j < LOUT && (k0 + s2 * L < bi.out_count)) ybuf[s2 * RY + (j % RY)] = sacc;
+    };
+
     // ---- epilogue of one finished super-iteration: Q outputs per segment, one thread per output --------
     auto epilogue = [&](int sup) {
         if (t >= NSEG * Q) return;
         const int es = t / Q, er = t - es * Q;
         const int j = sup * Q + er - (Q - 1);           // 0 = the segment's leading output
         const int k = k0 + es * L - LEAD + j;           // output index within the block
-        if (j < LEAD || j >= LL || k >= bi.out_count) return;
-        const float2 y = ybuf[es * LL + j];
+        if (j < LEAD || j >= LOUT || k >= bi.out_count) return;
+        const float2 y = ybuf[es * LL + (SUPRED ? j % RY : j)];
         const long long oidx = ch * a.out_stride + bi.out_start + k;
         if (DEMOD) {
             const float cur = fast_arctan2_ref(y.y, y.x);
             float prev;
             if (use_override && es == 0 && j == 1) prev = s_misc[0];
             else {
-                const float2 yp = ybuf[es * LL + j - 1];
+                const float2 yp = ybuf[es * LL + (SUPRED ? (j - 1) % RY : j - 1)];
                 prev = fast_arctan2_ref(yp.y, yp.x);
             }
             a.audio[oidx] = fm_step_ref(cur, prev, a.phasor_speed);
@@ -380,11 +408,11 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
         const uint32_t parity = (uint32_t)(sup & 1);
 #pragma unroll
         for (int slot = 0; slot < NS; slot++) {
-            const int par = (sup * NS + slot) & 1;  // partial-buffer parity of this stage
+            const int par = SUPRED ? (sup & 1) : ((sup * NS + slot) & 1);  // partial-buffer parity of this stage
             mbar_wait(&mbar[slot], parity);
             if (seg_active) {
                 const unsigned char* xs_ = xme + slot * stage_bytes;
-                unsigned char* ps_ = pme + par * pbuf_half;
+                unsigned char* ps_ = pme + par * pbuf_half + (SUPRED ? slot * R * prow_bytes : 0u);
 #pragma unroll
                 for (int r = 0; r < R; r++) {
                     const int i = slot * R + r;     // row within the super-iteration: compile-time
@@ -422,9 +450,14 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
             }
             __syncthreads();                       // stage consumed, partials visible
             issue((sup + 1) * NS + slot, slot);    // refill the slot just drained
-            reduce_stage(sup * NS + slot, par);
-            // all of the previous super-iteration's outputs were parked before this barrier
-            if (slot == 0 && sup > 0) epilogue(sup - 1);
+            if (SUPRED) {
+                if (slot == NS - 1) reduce_super(sup);
+            } else {
+                reduce_stage(sup * NS + slot, par);
+            }
+            // all of the previous super-iteration's outputs were parked before this barrier (the two-level
+            // reduce of wide rows finishes them one stage later)
+            if (slot == (two_level ? 1 : 0) && sup > 0) epilogue(sup - 1);
         }
     }
     __syncthreads();
@@ -505,12 +538,12 @@ void decim_plan_destroy(DecimPlan* p) {
     delete p;
 }
 
-template <int Q, int DT, int NSEGT, bool ROT, bool DEMOD>
+template <int Q, int DT, int NSEGT, bool ROT, bool DEMOD, bool SUPRED>
 static int launch_decim_t(const DecimArgs& a, dim3 grid, int NT, size_t smem, cudaStream_t s) {
     // launch bounds pick the CTAs/SM that 96 registers per thread allow (640 threads per SM)
 #define QDSP_DECIM_LAUNCH(MAXT, MINB)                                                                          \
     {                                                                                                          \
-        auto kern = decim_kernel<Q, DT, NSEGT, ROT, DEMOD, MAXT, MINB>;                                        \
+        auto kern = decim_kernel<Q, DT, NSEGT, ROT, DEMOD, SUPRED, MAXT, MINB>;                                        \
         QDSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
         kern<<<grid, NT, smem, s>>>(a);                                                                        \
     }
@@ -558,29 +591,34 @@ int launch_decim(DecimPlan* plan, const float2* hist, int H, const float2* in, c
     const int per_tile = a.NSEG * a.L;
     dim3 grid((part.max_out + per_tile - 1) / per_tile, part.view.nblocks, nch);
     const size_t stage_bytes = (size_t)a.NSEG * a.R * a.D * sizeof(float2);
-    const size_t smem = (size_t)a.NSTAGE * stage_bytes + (size_t)2 * a.NSEG * a.R * (a.P | 1) * sizeof(float2) +
-                        (size_t)a.NSEG * (a.L + lead) * sizeof(float2) + 16 + a.NSTAGE * 8 + 64 +
-                        (a.P > 64 ? (size_t)2 * a.NSEG * a.R * 64 * sizeof(float2) : 0);
-    if (smem > 227 * 1024) {
-        set_last_error("decim: tile does not fit shared memory (%zu bytes)", smem);
+    const size_t smem_stage = (size_t)a.NSTAGE * stage_bytes + (size_t)2 * a.NSEG * a.R * (a.P | 1) * sizeof(float2) +
+                              (size_t)a.NSEG * (a.L + lead) * sizeof(float2) + 16 + a.NSTAGE * 8 + 64 +
+                              (a.P > 64 ? (size_t)2 * a.NSEG * a.R * 64 * sizeof(float2) : 0);
+    const size_t smem_sup = (size_t)a.NSTAGE * stage_bytes + (size_t)2 * a.NSEG * plan->Q * (a.P | 1) * sizeof(float2) +
+                            (size_t)a.NSEG * 4 * plan->Q * sizeof(float2) + 16 + a.NSTAGE * 8 + 64;
+    if (smem_stage > 227 * 1024) {
+        set_last_error("decim: tile does not fit shared memory (%zu bytes)", smem_stage);
         return -1;
     }
     const bool fused = mode == 1;
+    static const bool supred_env = getenv("QDSP_DECIM_SUPRED") ? atoi(getenv("QDSP_DECIM_SUPRED")) != 0 : true;
+    const bool supred = supred_env && plan->P <= 64 && plan->NT >= 2 * plan->NSEG * plan->Q;
+    const size_t smem = supred ? smem_sup : smem_stage;
     if (plan->Q == 9 && plan->D == 50 && plan->NSEG == 12)   // config 2: 2.4 MS/s -> 48 kS/s, 401 taps
-        return fused ? launch_decim_t<9, 50, 12, true, true>(a, grid, plan->NT, smem, s)
-                     : launch_decim_t<9, 50, 12, false, false>(a, grid, plan->NT, smem, s);
+        return fused ? (supred ? launch_decim_t<9, 50, 12, true, true, true>(a, grid, plan->NT, smem, s) : launch_decim_t<9, 50, 12, true, true, false>(a, grid, plan->NT, smem, s))
+                     : (supred ? launch_decim_t<9, 50, 12, false, false, true>(a, grid, plan->NT, smem, s) : launch_decim_t<9, 50, 12, false, false, false>(a, grid, plan->NT, smem, s));
     if (plan->Q == 9 && plan->D == 50 && plan->NSEG == 6)
-        return fused ? launch_decim_t<9, 50, 6, true, true>(a, grid, plan->NT, smem, s)
-                     : launch_decim_t<9, 50, 6, false, false>(a, grid, plan->NT, smem, s);
+        return fused ? (supred ? launch_decim_t<9, 50, 6, true, true, true>(a, grid, plan->NT, smem, s) : launch_decim_t<9, 50, 6, true, true, false>(a, grid, plan->NT, smem, s))
+                     : (supred ? launch_decim_t<9, 50, 6, false, false, true>(a, grid, plan->NT, smem, s) : launch_decim_t<9, 50, 6, false, false, false>(a, grid, plan->NT, smem, s));
     if (plan->Q == 9 && plan->D == 50 && plan->NSEG == 5)
-        return fused ? launch_decim_t<9, 50, 5, true, true>(a, grid, plan->NT, smem, s)
-                     : launch_decim_t<9, 50, 5, false, false>(a, grid, plan->NT, smem, s);
+        return fused ? (supred ? launch_decim_t<9, 50, 5, true, true, true>(a, grid, plan->NT, smem, s) : launch_decim_t<9, 50, 5, true, true, false>(a, grid, plan->NT, smem, s))
+                     : (supred ? launch_decim_t<9, 50, 5, false, false, true>(a, grid, plan->NT, smem, s) : launch_decim_t<9, 50, 5, false, false, false>(a, grid, plan->NT, smem, s));
     if (plan->Q == 9)
-        return fused ? launch_decim_t<9, 0, 0, true, true>(a, grid, plan->NT, smem, s)
-                     : launch_decim_t<9, 0, 0, false, false>(a, grid, plan->NT, smem, s);
+        return fused ? (supred ? launch_decim_t<9, 0, 0, true, true, true>(a, grid, plan->NT, smem, s) : launch_decim_t<9, 0, 0, true, true, false>(a, grid, plan->NT, smem, s))
+                     : (supred ? launch_decim_t<9, 0, 0, false, false, true>(a, grid, plan->NT, smem, s) : launch_decim_t<9, 0, 0, false, false, false>(a, grid, plan->NT, smem, s));
     if (plan->Q == 6)
-        return fused ? launch_decim_t<6, 0, 0, true, true>(a, grid, plan->NT, smem, s)
-                     : launch_decim_t<6, 0, 0, false, false>(a, grid, plan->NT, smem, s);
+        return fused ? (supred ? launch_decim_t<6, 0, 0, true, true, true>(a, grid, plan->NT, smem, s) : launch_decim_t<6, 0, 0, true, true, false>(a, grid, plan->NT, smem, s))
+                     : (supred ? launch_decim_t<6, 0, 0, false, false, true>(a, grid, plan->NT, smem, s) : launch_decim_t<6, 0, 0, false, false, false>(a, grid, plan->NT, smem, s));
     set_last_error("decim: unsupported Q=%d", plan->Q);
     return -1;
 }
