@@ -202,6 +202,7 @@ struct qdsp_resamp {
     History hist;
     Partition part;
     DecimPlan* plan = nullptr;
+    FirDecimPlan* fplan = nullptr;   // small decimation (2..8): dense polyphase kernel
     int variant = 0;
 };
 
@@ -227,6 +228,7 @@ void qdsp_resamp_destroy(qdsp_resamp* h) {
     if (!h) return;
     if (h->phases_dev) cudaFree(h->phases_dev);
     if (h->plan) decim_plan_destroy(h->plan);
+    if (h->fplan) fir_decim_plan_destroy(h->fplan);
     h->hist.release();
     delete h;
 }
@@ -243,6 +245,10 @@ int qdsp_resamp_set_taps(qdsp_resamp* h, const float* taps, int tapCount) {
     h->plan = nullptr;
     if (h->dtype == QDSP_CF32 && decim_plan_supported(tapCount, h->interp, h->decim))
         h->plan = decim_plan_create(taps, tapCount, h->decim);
+    if (h->fplan) fir_decim_plan_destroy(h->fplan);
+    h->fplan = nullptr;
+    if (h->dtype == QDSP_CF32 && !h->plan && h->interp == 1 && h->decim >= 2 && h->decim <= 8)
+        h->fplan = fir_decim_plan_create(taps, tapCount, h->decim);
     return 0;
 }
 int qdsp_resamp_taps_per_phase(qdsp_resamp* h) { return h->tpp; }
@@ -264,7 +270,20 @@ long long qdsp_resamp_process(qdsp_resamp* h, const void* in_dev, void* out_dev,
     }
     if (count == 0) return 0;
     int rc;
-    if (h->plan && h->variant != 1) {
+    // the dense polyphase kernel works on a uniform output grid: every run() block but the last must be a
+    // multiple of D (otherwise the reference's per-block schedule restart shifts the grid: generic kernel)
+    bool regular = h->fplan != nullptr && h->variant != 1;
+    if (regular) {
+        if (blocks) {
+            for (int b = 0; b + 1 < nblocks && regular; b++) regular = (blocks[b] % h->decim) == 0;
+        } else {
+            regular = h->part.view.nblocks <= 1 || (h->part.view.block_size % h->decim) == 0;
+        }
+    }
+    if (regular) {
+        rc = launch_fir_decim(h->fplan, (const float2*)h->hist.ptr(), h->hist.H, (const float2*)in_dev, count,
+                              h->part.total_out, (float2*)out_dev, s);
+    } else if (h->plan && h->variant != 1) {
         rc = launch_decim(h->plan, (const float2*)h->hist.ptr(), h->hist.H, (const float2*)in_dev, h->part, 0, nullptr,
                           0, 1, 0.0f, nullptr, nullptr, (float2*)out_dev, nullptr, 0, s);
     } else if (h->dtype == QDSP_CF32) {

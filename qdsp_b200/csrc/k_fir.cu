@@ -130,6 +130,140 @@ fir_dense_kernel(VStream<float2> xs, long long count, const float2* __restrict__
     }
 }
 
+// =================================================================================================
+// Decimating variant (PolyphaseResampler with interp = 1 and a small decimation D, e.g. config 1b: D = 4,
+// 127 taps): y[k] = sum_t h[t] * x[D*k + t - T]  (reference src/dsp/resampling.h:121-125 with I = 1).
+// The input is split into its D polyphase sub-streams x_r[m] = x[base + D*m + r] while it is staged, each
+// sub-stream is a dense FIR with taps h_r[q] = h[D*q + r], and all D sub-filters accumulate into the same
+// 9 register-blocked outputs per thread -- the inner loop is the dense kernel's (one 128-bit shared load
+// + one broadcast tap load per 18 FFMA2, conflict-free lane stride).
+// =================================================================================================
+struct FirDecimPlan {
+    int T = 0, D = 0;
+    int U = 0;                   // tap pairs per (sub-stream, parity) table, multiple of kFirR
+    float2* taps_dev = nullptr;  // [D][2][U]
+};
+
+FirDecimPlan* fir_decim_plan_create(const float* taps, int T, int D) {
+    if (T < 2 || D < 2 || D > 8) return nullptr;
+    const int tq = (T + D - 1) / D;              // taps of the longest sub-filter
+    int U = (tq + 2) / 2;
+    U = ((U + kFirR - 1) / kFirR) * kFirR;
+    const size_t smem = (size_t)D * (kFirNout / 2 + U + 8) * 16 + (size_t)D * 2 * U * 8;
+    if (smem > 110 * 1024) return nullptr;       // keep two CTAs per SM
+    FirDecimPlan* p = new (std::nothrow) FirDecimPlan();
+    if (!p) return nullptr;
+    p->T = T;
+    p->D = D;
+    p->U = U;
+    std::vector<float2> tab((size_t)D * 2 * U, make_float2(0.f, 0.f));
+    for (int r = 0; r < D; r++) {
+        auto h = [&](int q) {
+            const int t = D * q + r;
+            return (q >= 0 && t < T) ? taps[t] : 0.0f;
+        };
+        for (int u = 0; u < U; u++) {
+            tab[((size_t)r * 2 + 0) * U + u] = make_float2(h(2 * u), h(2 * u + 1));
+            tab[((size_t)r * 2 + 1) * U + u] = make_float2(h(2 * u - 1), h(2 * u));
+        }
+    }
+    if (cudaMalloc(&p->taps_dev, tab.size() * sizeof(float2)) != cudaSuccess ||
+        cudaMemcpy(p->taps_dev, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_last_error("fir_decim_plan_create: tap upload failed");
+        delete p;
+        return nullptr;
+    }
+    return p;
+}
+void fir_decim_plan_destroy(FirDecimPlan* p) {
+    if (!p) return;
+    if (p->taps_dev) cudaFree(p->taps_dev);
+    delete p;
+}
+
+__global__ void __launch_bounds__(kFirThreads, 2)
+fir_decim_kernel(VStream<float2> xs, long long count, long long n_out, const float2* __restrict__ taps, int T, int D,
+                 int U, float2* __restrict__ out) {
+    constexpr int R = kFirR;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int npairs = kFirNout / 2 + U + 8;                         // per sub-stream
+    float4* sq = reinterpret_cast<float4*>(smem_raw);                 // [D][npairs] sample quads
+    float2* st = reinterpret_cast<float2*>(smem_raw + (size_t)D * npairs * 16);  // [D][2][U]
+    const int t = threadIdx.x;
+    const long long k_t = (long long)blockIdx.x * kFirNout;           // first output of the tile
+    const long long B = (long long)D * k_t - T;                       // sample index of sub-stream 0, element 0
+
+    for (int i = t; i < D * 2 * U; i += kFirThreads) st[i] = taps[i];
+    {
+        float* sf = reinterpret_cast<float*>(sq);
+        const int nsamp = 2 * npairs * D;                             // consecutive input samples of the tile
+        for (int e = t; e < nsamp; e += kFirThreads) {
+            const long long i = B + e;
+            const float2 v = (i < count) ? xs.at(i) : make_float2(0.f, 0.f);
+            const int r = e % D, m = e / D;                           // sub-stream, index within it
+            const int q = m >> 1, h = m & 1;
+            sf[((size_t)r * npairs + q) * 4 + h] = v.x;
+            sf[((size_t)r * npairs + q) * 4 + 2 + h] = v.y;
+        }
+    }
+    __syncthreads();
+
+    const int w = t >> 5, lane = t & 31;
+    const int parity = w & 1, wp = w >> 1;
+    const int j0 = wp * 32 * R + lane * R;
+    float2 accRe[R], accIm[R];
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+        accRe[i] = make_float2(0.f, 0.f);
+        accIm[i] = make_float2(0.f, 0.f);
+    }
+#pragma unroll 1
+    for (int r = 0; r < D; r++) {
+        const float2* tt = st + ((size_t)r * 2 + parity) * U;
+        const float4* win = sq + (size_t)r * npairs + j0;
+        float4 W[R];
+#pragma unroll
+        for (int i = 0; i < R; i++) W[i] = win[i];
+#pragma unroll 1
+        for (int u0 = 0; u0 < U; u0 += R) {
+#pragma unroll
+            for (int k = 0; k < R; k++) {
+                const float2 hh = tt[u0 + k];
+#pragma unroll
+                for (int i = 0; i < R; i++) {
+                    const float4 s = W[(k + i) % R];
+                    accRe[i] = __ffma2_rn(make_float2(s.x, s.y), hh, accRe[i]);
+                    accIm[i] = __ffma2_rn(make_float2(s.z, s.w), hh, accIm[i]);
+                }
+                W[k] = win[u0 + k + R];
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+        const long long k = k_t + 2 * (long long)(j0 + i) + parity;
+        if (k < n_out) out[k] = make_float2(accRe[i].x + accRe[i].y, accIm[i].x + accIm[i].y);
+    }
+}
+
+// count input samples (one regular partition: every run() block a multiple of D, so the output grid is uniform)
+int launch_fir_decim(FirDecimPlan* plan, const float2* hist, int H, const float2* in, long long count,
+                     long long n_out, float2* out, cudaStream_t s) {
+    if (n_out <= 0) return 0;
+    VStream<float2> xs{hist, in, H};
+    const size_t smem = (size_t)plan->D * (kFirNout / 2 + plan->U + 8) * 16 + (size_t)plan->D * 2 * plan->U * 8;
+    static bool attr_set = false;
+    if (!attr_set) {
+        QDSP_CUDA_OK(cudaFuncSetAttribute(fir_decim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        attr_set = true;
+    }
+    const long long tiles = (n_out + kFirNout - 1) / kFirNout;
+    fir_decim_kernel<<<(unsigned)tiles, kFirThreads, smem, s>>>(xs, count, n_out, plan->taps_dev, plan->T, plan->D,
+                                                                plan->U, out);
+    QDSP_LAUNCH_OK();
+    return 0;
+}
+
 int launch_fir_dense(FirPlan* plan, const float2* hist, int H, const float2* in, long long count, int lead,
                      float2* out, cudaStream_t s) {
     if (count <= 0) return 0;

@@ -50,6 +50,13 @@ void fir_plan_destroy(FirPlan* p);
 int launch_fir_dense(FirPlan* plan, const float2* hist, int H, const float2* in, long long count, int lead,
                      float2* out, cudaStream_t s);
 
+// small-decimation FIR (interp = 1, 2 <= D <= 8): polyphase sub-streams through the dense inner loop
+struct FirDecimPlan;
+FirDecimPlan* fir_decim_plan_create(const float* taps, int T, int D);
+void fir_decim_plan_destroy(FirDecimPlan* p);
+int launch_fir_decim(FirDecimPlan* plan, const float2* hist, int H, const float2* in, long long count,
+                     long long n_out, float2* out, cudaStream_t s);
+
 // ---- k_recurrent.cu -----------------------------------------------------------------------------
 int launch_deemp(const float2* in, float2* out, long long count, float alpha, float* state, void* scratch,
                  size_t scratch_bytes, cudaStream_t s);
