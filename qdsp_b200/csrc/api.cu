@@ -750,7 +750,7 @@ struct qdsp_ffagc {
 struct qdsp_costas {
     int order = 4;
     float alpha = 0.0f, beta = 0.0f;
-    int chunk = 16384, warmup = 4096;
+    int chunk = 8192, warmup = 4096;
     DevState st;   // [4] state + [1] residual
     Scratch scratch;
 };
@@ -806,9 +806,10 @@ long long qdsp_agc_process(qdsp_agc* h, const float* in_dev, float* out_dev, lon
     if (h->part.build(count, blocks, nblocks, block_size, 1, 1, s) != 0) return -1;
     const int nb = h->part.view.nblocks;
     if (nb == 0) return 0;
-    if (h->scratch.reserve(sizeof(float) * 2 * (size_t)nb + 64) != 0) return -1;
+    // scratch: [nb][32] partial maxima of the block-max pass, then [nb] reciprocal levels
+    if (h->scratch.reserve(sizeof(float) * 33 * (size_t)nb + 64) != 0) return -1;
     float* bm = (float*)h->scratch.p;
-    if (launch_agc(in_dev, out_dev, h->part, h->corrected, h->st.p, bm, bm + nb, s) != 0) return -1;
+    if (launch_agc(in_dev, out_dev, h->part, h->corrected, h->st.p, bm, bm + 32 * (size_t)nb, s) != 0) return -1;
     return count;
 }
 int qdsp_agc_get_state(qdsp_agc* h, float* level) { return h->st.get(level, 1); }
