@@ -64,7 +64,7 @@ namespace dsp {
             qdsp_costas_set_chunking(h, _chunk, _warmup);
         }
         float _loopBandwidth = 1.0f;
-        int _chunk = 16384, _warmup = 4096;
+        int _chunk = 4096, _warmup = 4096;
         stream<complex_t>* _in = nullptr;
         qdsp_costas* h = nullptr;
     };

@@ -750,7 +750,7 @@ struct qdsp_ffagc {
 struct qdsp_costas {
     int order = 4;
     float alpha = 0.0f, beta = 0.0f;
-    int chunk = 8192, warmup = 4096;
+    int chunk = 4096, warmup = 4096;
     DevState st;   // [4] state + [1] residual
     Scratch scratch;
 };

@@ -327,3 +327,15 @@ def test_channelizer_config4_geometry(variant):
         a64, _ = P.vfo_fm(off, 61.44e6, 48e3, 48e3, 5e3, x, blk, nco_f64=True)
         assert y[c].shape == a64.shape
         assert np.abs(y[c][16:] - a64[16:]).max() <= AUDIO_TOL, (c, np.abs(y[c][16:] - a64[16:]).max())
+
+
+def test_costas_default_chunking_long():
+    # the library's default chunking (chunk 4096, warm-up 4096) on 2^20 QPSK samples vs the sequential oracle
+    from qdsp_b200 import blocks as B, synth
+
+    x = synth.qpsk_cf32(33, 0, 1 << 20)
+    yo, _ = loader.port().costas(4, 0.004, x)
+    pl = B.CostasLoop(4, 0.004)
+    y = pl.process(x)
+    assert pl.last_residual() < 1e-3
+    assert np.abs(y - yo).max() <= 1e-4, np.abs(y - yo).max()

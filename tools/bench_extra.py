@@ -96,10 +96,10 @@ def main():
         x = uniform(n, 5)
         y = torch.empty(n, dtype=torch.complex64, device="cuda")
         for name, blk, bytes_per in [("BFMDeemp", B.BFMDeemp(48e3, 50e-6), 16), ("ComplexAGC", B.ComplexAGC(1.0, 65535.0, 1e-3), 16),
-                                     ("CostasLoop<4> chunk 8192 warmup 4096", B.CostasLoop(4, 0.004), 16),
+                                     ("CostasLoop<4> chunk 4096 warmup 4096", B.CostasLoop(4, 0.004), 16),
                                      ("FeedForwardAGC", B.FeedForwardAGC(), 16), ("FrequencyXlator", B.FrequencyXlator(FS, -250e3), 16)]:
             if "Costas" in name:
-                blk.set_chunking(8192, 4096)
+                blk.set_chunking(4096, 4096)
             ms = timed(lambda: blk.process_device(x.data_ptr(), y.data_ptr(), n, stream=sp), args.steps, warmup=1)
             print(json.dumps({"config": f"5 {name}, {n} elements", "ms": ms, "Msamples_s": n / ms / 1e3,
                               "hbm_gbs": bytes_per * n / ms / 1e6, "frac_hbm_measured": bytes_per * n / ms / 1e6 / hbm}), flush=True)
