@@ -103,6 +103,19 @@ __device__ float2 direct_output_warp(const DecimArgs& a, long long win_start, ui
     return acc;
 }
 
+// shared-memory pitches (used by the kernel and by the launcher's size computation)
+__host__ __device__ inline int decim_seg_pad(int D) {
+    // chunk = R*D samples; pad (in samples, even) so that pitch*8 == D*8 (mod 128)
+    const int want = (D * 8) % 128, have = (3 * D * 8) % 128;
+    const int pad_bytes = ((want - have) % 128 + 128) % 128;
+    return pad_bytes / 8;   // D even => both residues are multiples of 16: pad is an even sample count
+}
+__host__ __device__ inline int decim_ppad_sup(int P) {
+    int p = P;
+    while ((p & 3) != 2) p++;
+    return p;
+}
+
 // packed f32x2 helpers for the two-column phasor recurrence
 __device__ __forceinline__ float2 neg2(float2 v) { return make_float2(-v.x, -v.y); }
 
@@ -125,8 +138,13 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
     // ---- shared memory carve-up (byte offsets from the dynamic base) ---------------------------
     const int chunk_elems = R * D;                                   // per segment per stage
     const uint32_t chunk_bytes = (uint32_t)chunk_elems * 8u;
-    const uint32_t stage_bytes = (uint32_t)NSEG * chunk_bytes;
-    const int Ppad = P | 1;
+    // segment pitch in a ring slot: padded so that a warp whose lanes straddle two segments keeps walking
+    // consecutive 16-byte bank groups (pitch == row bytes mod 128)
+    const int seg_pitch = chunk_elems + decim_seg_pad(D);
+    const uint32_t stage_bytes = (uint32_t)NSEG * (uint32_t)seg_pitch * 8u;
+    // partial-buffer row pitch: odd for the 8-lane per-stage reduce; == 2 (mod 4) for the 2-lane SUPRED reduce
+    // (lane pairs read 16 contiguous bytes, 16 rows land on 8 distinct 16-byte bank groups: 2 wavefronts)
+    const int Ppad = SUPRED ? decim_ppad_sup(P) : (P | 1);
     // SUPRED (narrow rows): partials of a whole super-iteration (Q rows) are kept and reduced once per
     // super-iteration by 2 lanes per output; otherwise per stage (R rows) by 8 lanes per output
     constexpr int PROWS = SUPRED ? Q : R;
@@ -202,7 +220,7 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
 
     // ---- producer: warp 0, lane l issues segment l's TMA bulk copy; one mbarrier arrival per stage ----
     // (edge tiles -- history before sample 0 or the ragged end of the buffer -- also run the guarded fill)
-    float2* xseg = X + (size_t)seg * chunk_elems;
+    float2* xseg = X + (size_t)seg * seg_pitch;
     const int nactive = (bi.out_count - k0 + L - 1) / L < NSEG ? (bi.out_count - k0 + L - 1) / L : NSEG;
     const long long tile_first = bi.in_start + (long long)(k0 - LEAD) * D - a.T - pad;
     const long long tile_last = tile_first + (long long)(nactive - 1) * L * D + (long long)nst * chunk_elems;
@@ -217,7 +235,7 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
         p_lo = (int)(lo < nst ? lo : nst);
         p_hi = (int)(hi < nst ? hi : nst);
         p_gsrc = a.in + pbase;
-        p_dst = reinterpret_cast<unsigned char*>(X + (size_t)t * chunk_elems);
+        p_dst = reinterpret_cast<unsigned char*>(X + (size_t)t * seg_pitch);
     }
     auto issue = [&](int it, int slot) {
         if (t < 32) {
@@ -590,11 +608,11 @@ int launch_decim(DecimPlan* plan, const float2* hist, int H, const float2* in, c
     a.out_stride = out_stride;
     const int per_tile = a.NSEG * a.L;
     dim3 grid((part.max_out + per_tile - 1) / per_tile, part.view.nblocks, nch);
-    const size_t stage_bytes = (size_t)a.NSEG * a.R * a.D * sizeof(float2);
+    const size_t stage_bytes = (size_t)a.NSEG * (a.R * a.D + decim_seg_pad(a.D)) * sizeof(float2);
     const size_t smem_stage = (size_t)a.NSTAGE * stage_bytes + (size_t)2 * a.NSEG * a.R * (a.P | 1) * sizeof(float2) +
                               (size_t)a.NSEG * (a.L + lead) * sizeof(float2) + 16 + a.NSTAGE * 8 + 64 +
                               (a.P > 64 ? (size_t)2 * a.NSEG * a.R * 64 * sizeof(float2) : 0);
-    const size_t smem_sup = (size_t)a.NSTAGE * stage_bytes + (size_t)2 * a.NSEG * plan->Q * (a.P | 1) * sizeof(float2) +
+    const size_t smem_sup = (size_t)a.NSTAGE * stage_bytes + (size_t)2 * a.NSEG * plan->Q * decim_ppad_sup(a.P) * sizeof(float2) +
                             (size_t)a.NSEG * 4 * plan->Q * sizeof(float2) + 16 + a.NSTAGE * 8 + 64;
     if (smem_stage > 227 * 1024) {
         set_last_error("decim: tile does not fit shared memory (%zu bytes)", smem_stage);
