@@ -339,3 +339,49 @@ def test_costas_default_chunking_long():
     y = pl.process(x)
     assert pl.last_residual() < 1e-3
     assert np.abs(y - yo).max() <= 1e-4, np.abs(y - yo).max()
+
+
+def test_edge_cases_empty_and_tiny_inputs():
+    # empty calls, inputs shorter than one decimation period / one filter length, single-sample calls
+    from qdsp_b200 import blocks as B, synth
+
+    P = loader.port()
+    x = synth.cfg2_input(0, 3000)
+    v = B.VFOFM(250e3, 2.4e6, 48e3, 48e3, 5e3)
+    assert len(v.process(x[:0])) == 0
+    parts = [v.process(x[:7], 7), v.process(x[7:49], 42), v.process(x[49:50], 1), v.process(x[50:1000], 950), v.process(x[1000:], 2000)]
+    y = np.concatenate(parts)
+    ref, oc = P.vfo_fm(250e3, 2.4e6, 48e3, 48e3, 5e3, x, [7, 42, 1, 950, 2000])
+    assert [len(p) for p in parts] == list(oc)
+    assert y.shape == ref.shape and np.abs(y[8:] - ref[8:]).max() <= AUDIO_TOL
+    r = B.PolyphaseResampler(B.BlackmanWindow(300e3, 4 * 2.4e6 / 127, 2.4e6), 2.4e6, 0.6e6)
+    xu = synth.uniform_cf32(1, 0, 1000)
+    assert len(r.process(xu[:0])) == 0
+    got = np.concatenate([r.process(xu[:3], 3), r.process(xu[3:4], 1), r.process(xu[4:8], 4), r.process(xu[8:], 992)])
+    taps = P.blackman_taps(300e3, 4 * 2.4e6 / 127, 2.4e6)
+    want, oc = P.resamp_cf32(taps, 1, 4, xu, [3, 1, 4, 992])
+    assert got.shape == want.shape and rel_l2(got, want) <= IQ_TOL
+    f = B.FIR(B.BlackmanWindow(300e3, 4 * 2.4e6 / 127, 2.4e6), np.float32)
+    xf = synth.uniform_f32(11, 0, 300)
+    yf = np.concatenate([f.process(xf[:1]), f.process(xf[1:2]), f.process(xf[2:])])
+    assert rel_l2(yf, P.fir_f32(taps, xf)) <= IQ_TOL
+    for blk in (B.BFMDeemp(48e3, 50e-6), B.ComplexAGC(1.0, 65535.0, 1e-3), B.CostasLoop(4, 0.004), B.FrequencyXlator(2.4e6, 1e3)):
+        assert len(blk.process(xu[:0])) == 0
+        assert len(blk.process(xu[:1])) == 1
+
+
+def test_vfo_set_offset_keeps_phase_continuous_and_reset():
+    from qdsp_b200 import blocks as B, synth
+
+    x = synth.cfg2_input(0, 40000)
+    v = B.VFOFM(250e3, 2.4e6, 48e3, 48e3, 5e3)
+    a = v.process(x, 10000)
+    v.reset()
+    b = v.process(x, 10000)
+    assert np.array_equal(a, b), "reset() must restore the initial state exactly"
+    # retuning to the same offset must be a no-op for the NCO phase
+    v.reset()
+    c1 = v.process(x[:20000], 10000)
+    v.setOffset(250e3)
+    c2 = v.process(x[20000:], 10000)
+    assert np.abs(np.concatenate([c1, c2]) - a).max() <= 1e-6
