@@ -28,7 +28,12 @@ namespace qdsp {
 struct DecimPlan {
     int T = 0, D = 0, Q = 0, P = 0;
     int NSEG = 0, R = 0, NSTAGE = 0, NSUP = 0, NT = 0;
-    float2* taps_dev = nullptr;  // [2][Q][P] tap pairs for pad = 0 / 1 (g[t] = h[t - pad])
+    // wide rows are cut into column slices of `D` samples each (DS = full decimation = global row stride); every
+    // slice is an independent CTA stream producing partial outputs that finish_kernel sums (and demodulates)
+    int DS = 0, nslices = 1;
+    float2* taps_dev = nullptr;  // [nslices][2][Q][P] tap pairs for pad = 0 / 1 (g[t] = h[t - pad])
+    float2* ypart = nullptr;     // [nch * nslices][ypart_stride] partial outputs (sliced plans only)
+    size_t ypart_cap = 0;
 };
 
 struct DecimArgs {
@@ -39,6 +44,7 @@ struct DecimArgs {
     const float2* taps;  // [2][Q][P]
     PartitionDev part;
     int T, D, P, NSEG, R, NSTAGE, NSUP, L;
+    int DS, nslices;     // global row stride (full decimation) and column slices per row (1 = unsliced)
     const NcoDev* nco;
     long long abs0;
     float phasor_speed;
@@ -130,13 +136,19 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
     const int NSEG = NSEGT ? NSEGT : a.NSEG;     // all shared-memory offsets fold into immediates
     const int P = D / 2, L = a.L;
     const int t = threadIdx.x;
-    const int b = blockIdx.y, ch = blockIdx.z;
+    const int b = blockIdx.y;
+    const int ch = blockIdx.z / a.nslices, slice = blockIdx.z - ch * a.nslices;
+    const int plane = blockIdx.z;                // output plane: channel, or (channel, slice) for sliced rows
+    const int DSg = a.DS;                        // global row stride; == D unless the rows are sliced
+    const long long col_off = (long long)slice * D;
     const BlkInfo bi = a.part.get(b);
     const int k0 = blockIdx.x * (NSEG * L);
     if (k0 >= bi.out_count) return;
 
     // ---- shared memory carve-up (byte offsets from the dynamic base) ---------------------------
     const int chunk_elems = R * D;                                   // per segment per stage
+    const long long chunk_span = (long long)R * a.DS;                // global samples one stage advances
+    const long long chunk_tail = (long long)(R - 1) * a.DS + D;      // samples from a chunk's first to past its last
     const uint32_t chunk_bytes = (uint32_t)chunk_elems * 8u;
     // segment pitch in a ring slot: padded so that a warp whose lanes straddle two segments keeps walking
     // consecutive 16-byte bank groups (pitch == row bytes mod 128)
@@ -167,7 +179,7 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
     const bool in_grid = seg < NSEG;
     const int pad = (int)((bi.in_start - a.T) & 1);
     const int ks = k0 + seg * L - LEAD;  // first output (the leading one when DEMOD) of this segment
-    const long long seg_base = bi.in_start + (long long)ks * D - a.T - pad;
+    const long long seg_base = bi.in_start + (long long)ks * DSg - a.T - pad + col_off;
     const bool seg_active = in_grid && (k0 + seg * L < bi.out_count);
     // rows this CTA really needs: its fullest segment (segment 0) has min(L, out_count - k0) outputs
     const int need = (bi.out_count - k0 < L ? bi.out_count - k0 : L) + LEAD + Q - 1;
@@ -178,8 +190,9 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
     int fast_lo = 0, fast_hi = 0, live_hi = 0;
     if (seg_active) {
         live_hi = nst;
-        const long long lo = seg_base >= 0 ? 0 : (-seg_base + chunk_elems - 1) / chunk_elems;
-        const long long hi = a.n_in - seg_base < 0 ? 0 : (a.n_in - seg_base) / chunk_elems;
+        const long long lo = seg_base >= 0 ? 0 : (-seg_base + chunk_span - 1) / chunk_span;
+        const long long room = a.n_in - seg_base - chunk_tail;    // chunks that end inside the buffer
+        const long long hi = room < 0 ? 0 : room / chunk_span + 1;
         fast_lo = (int)(lo < nst ? lo : nst);
         fast_hi = (int)(hi < nst ? hi : nst);
     }
@@ -207,11 +220,11 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
         if (pb < 0) {
             use_override = true;
             if (t == 0) s_misc[0] = a.demod_in[ch];
-        } else if (pb != b - 1 || pbi.in_start + (long long)pbi.out_count * D != bi.in_start) {
+        } else if (pb != b - 1 || pbi.in_start + (long long)pbi.out_count * DSg != bi.in_start) {
             use_override = true;  // previous block's last output is off this block's row grid
             if (t < 32) {
                 const float2 y = direct_output_warp<ROT>(
-                    a, pbi.in_start + (long long)(pbi.out_count - 1) * D - a.T, nco_ph0, nco_step);
+                    a, pbi.in_start + (long long)(pbi.out_count - 1) * DSg - a.T, nco_ph0, nco_step);
                 if (t == 0) s_misc[0] = fast_arctan2_ref(y.y, y.x);
             }
         }
@@ -222,16 +235,17 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
     // (edge tiles -- history before sample 0 or the ragged end of the buffer -- also run the guarded fill)
     float2* xseg = X + (size_t)seg * seg_pitch;
     const int nactive = (bi.out_count - k0 + L - 1) / L < NSEG ? (bi.out_count - k0 + L - 1) / L : NSEG;
-    const long long tile_first = bi.in_start + (long long)(k0 - LEAD) * D - a.T - pad;
-    const long long tile_last = tile_first + (long long)(nactive - 1) * L * D + (long long)nst * chunk_elems;
+    const long long tile_first = bi.in_start + (long long)(k0 - LEAD) * DSg - a.T - pad + col_off;
+    const long long tile_last = tile_first + (long long)(nactive - 1) * L * DSg + (long long)(nst - 1) * chunk_span + chunk_tail;
     const bool edge_tile = tile_first < 0 || tile_last > a.n_in;
     const float2* p_gsrc = nullptr;     // producer lane's segment
     int p_lo = 0, p_hi = 0;
     unsigned char* p_dst = nullptr;
     if (t < 32 && t < nactive) {
-        const long long pbase = tile_first + (long long)t * L * D;
-        const long long lo = pbase >= 0 ? 0 : (-pbase + chunk_elems - 1) / chunk_elems;
-        const long long hi = a.n_in - pbase < 0 ? 0 : (a.n_in - pbase) / chunk_elems;
+        const long long pbase = tile_first + (long long)t * L * DSg;
+        const long long lo = pbase >= 0 ? 0 : (-pbase + chunk_span - 1) / chunk_span;
+        const long long room = a.n_in - pbase - chunk_tail;
+        const long long hi = room < 0 ? 0 : room / chunk_span + 1;
         p_lo = (int)(lo < nst ? lo : nst);
         p_hi = (int)(hi < nst ? hi : nst);
         p_gsrc = a.in + pbase;
@@ -243,16 +257,25 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
             const unsigned m = __ballot_sync(0xffffffffu, fast);
             if (t == 0) mbar_arrive_expect_tx(&mbar[slot], (uint32_t)__popc(m) * chunk_bytes);
             __syncwarp();
-            if (fast) tma_bulk_g2s(p_dst + slot * stage_bytes, p_gsrc + (size_t)it * chunk_elems, chunk_bytes, &mbar[slot]);
+            if (fast) {
+                if (DSg == D) {
+                    tma_bulk_g2s(p_dst + slot * stage_bytes, p_gsrc + (size_t)it * chunk_elems, chunk_bytes, &mbar[slot]);
+                } else {   // sliced rows: one bulk copy per row (row stride DSg in memory, D contiguous samples)
+                    for (int rr = 0; rr < R; rr++)
+                        tma_bulk_g2s(p_dst + slot * stage_bytes + (size_t)rr * D * 8, p_gsrc + ((size_t)it * R + rr) * DSg,
+                                     (uint32_t)D * 8u, &mbar[slot]);
+                }
+            }
         }
         if (edge_tile && in_grid) {
             const bool fast = it >= fast_lo && it < fast_hi;
             if (!fast && it < live_hi) {
                 VStream<float2> xs{a.hist, a.in, a.H};
                 float2* dst = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(xseg) + slot * stage_bytes);
-                const long long start = seg_base + (long long)it * chunk_elems;
+                const long long start = seg_base + (long long)it * chunk_span;
                 for (int e = pair; e < chunk_elems; e += P) {
-                    const long long i = start + e;
+                    const int rr = e / D;
+                    const long long i = start + (long long)rr * DSg + (e - rr * D);
                     dst[e] = (i < a.n_in) ? xs.at(i) : make_float2(0.f, 0.f);
                 }
             }
@@ -264,7 +287,7 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
 #pragma unroll
     for (int q = 0; q < Q; q++) tp[q] = make_float2(0.f, 0.f);
     if (in_grid) {
-        const float2* tt = a.taps + (size_t)pad * Q * P;
+        const float2* tt = a.taps + ((size_t)slice * 2 + pad) * Q * P;
 #pragma unroll
         for (int q = 0; q < Q; q++) tp[q] = tt[q * P + pair];
     }
@@ -273,7 +296,7 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
     float2 wr2 = make_float2(1.f, 1.f), wi2 = make_float2(0.f, 0.f);
     const long long col0 = seg_base + 2 * pair;  // sample index of (row 0, first column of the pair)
     if (ROT) {
-        const float2 w = phasor_from_turns(nco_step * (uint64_t)D);
+        const float2 w = phasor_from_turns(nco_step * (uint64_t)DSg);
         wr2 = make_float2(w.x, w.x);
         wi2 = make_float2(w.y, w.y);
     }
@@ -395,7 +418,7 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
         const int k = k0 + es * L - LEAD + j;           // output index within the block
         if (j < LEAD || j >= LOUT || k >= bi.out_count) return;
         const float2 y = ybuf[es * LL + (SUPRED ? j % RY : j)];
-        const long long oidx = ch * a.out_stride + bi.out_start + k;
+        const long long oidx = plane * a.out_stride + bi.out_start + k;
         if (DEMOD) {
             const float cur = fast_arctan2_ref(y.y, y.x);
             float prev;
@@ -417,7 +440,7 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
     for (int sup = 0; sup < nsup; sup++) {
         if (ROT && (sup & 7) == 0 && seg_active) {
             // exact phasor re-seed (closed form) every 8*Q rows bounds the recurrence's rounding walk
-            const long long i0 = col0 + (long long)sup * Q * D;
+            const long long i0 = col0 + (long long)sup * Q * DSg;
             const float2 p0 = phasor_from_turns(nco_ph0 + nco_step * (uint64_t)i0);
             const float2 p1 = phasor_from_turns(nco_ph0 + nco_step * (uint64_t)(i0 + 1));
             PR = make_float2(p0.x, p1.x);
@@ -513,8 +536,15 @@ DecimPlan* decim_plan_create(const float* taps, int T, int D) {
     DecimPlan* p = new (std::nothrow) DecimPlan();
     if (!p) return nullptr;
     p->T = T;
-    p->D = D;
-    p->P = D / 2;
+    p->DS = D;
+    p->nslices = 1;
+    // wide rows (config 4: D = 1280) are cut into 128-column slices: each slice is a narrow-row stream of its own
+    // (128-thread CTAs, 2-lane partial reduce) whose partial outputs finish_kernel sums
+    static const bool slice_env = getenv("QDSP_DECIM_SLICE") ? atoi(getenv("QDSP_DECIM_SLICE")) != 0 : true;
+    if (slice_env && D > 128 && D % 128 == 0) p->nslices = D / 128;
+    const int Dc = D / p->nslices;
+    p->D = Dc;
+    p->P = Dc / 2;
     p->Q = round_q((T + 1 + D - 1) / D);
     p->R = 3;
     p->NSTAGE = p->Q / 3;
@@ -532,16 +562,17 @@ DecimPlan* decim_plan_create(const float* taps, int T, int D) {
     if (p->NT < 64) p->NT = 64;
     p->NSUP = 29;
     if (const char* e = getenv("QDSP_DECIM_NSUP")) p->NSUP = atoi(e) > 1 ? atoi(e) : 29;
-    std::vector<float2> tab((size_t)2 * p->Q * p->P, make_float2(0.f, 0.f));
-    for (int pad = 0; pad < 2; pad++)
-        for (int q = 0; q < p->Q; q++)
-            for (int c = 0; c < p->P; c++) {
-                const int t0 = q * D + 2 * c - pad, t1 = t0 + 1;
-                float2 v;
-                v.x = (t0 >= 0 && t0 < T) ? taps[t0] : 0.0f;
-                v.y = (t1 >= 0 && t1 < T) ? taps[t1] : 0.0f;
-                tab[((size_t)pad * p->Q + q) * p->P + c] = v;
-            }
+    std::vector<float2> tab((size_t)p->nslices * 2 * p->Q * p->P, make_float2(0.f, 0.f));
+    for (int sl = 0; sl < p->nslices; sl++)
+        for (int pad = 0; pad < 2; pad++)
+            for (int q = 0; q < p->Q; q++)
+                for (int c = 0; c < p->P; c++) {
+                    const int t0 = q * D + sl * Dc + 2 * c - pad, t1 = t0 + 1;
+                    float2 v;
+                    v.x = (t0 >= 0 && t0 < T) ? taps[t0] : 0.0f;
+                    v.y = (t1 >= 0 && t1 < T) ? taps[t1] : 0.0f;
+                    tab[(((size_t)sl * 2 + pad) * p->Q + q) * p->P + c] = v;
+                }
     if (cudaMalloc(&p->taps_dev, tab.size() * sizeof(float2)) != cudaSuccess ||
         cudaMemcpy(p->taps_dev, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) {
         set_last_error("decim_plan_create: tap upload failed");
@@ -553,7 +584,43 @@ DecimPlan* decim_plan_create(const float* taps, int T, int D) {
 void decim_plan_destroy(DecimPlan* p) {
     if (!p) return;
     if (p->taps_dev) cudaFree(p->taps_dev);
+    if (p->ypart) cudaFree(p->ypart);
     delete p;
+}
+
+// sliced rows: sum the per-slice partial outputs; optionally apply the FM-demod epilogue (demodulator.h:87-94)
+__global__ void __launch_bounds__(256) decim_finish_kernel(const float2* __restrict__ ypart, long long ypart_stride,
+                                                          int nslices, long long total_out, int demod,
+                                                          float phasor_speed, const float* __restrict__ demod_in,
+                                                          float* __restrict__ demod_out, float2* __restrict__ out_iq,
+                                                          float* __restrict__ audio, long long out_stride) {
+    const int ch = blockIdx.y;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    auto total = [&](long long o) {
+        float2 y = make_float2(0.f, 0.f);
+        for (int sl = 0; sl < nslices; sl++) {
+            const float2 v = ypart[((size_t)ch * nslices + sl) * ypart_stride + o];
+            y.x += v.x;
+            y.y += v.y;
+        }
+        return y;
+    };
+    for (long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x; o < total_out; o += stride) {
+        const float2 y = total(o);
+        if (out_iq) out_iq[ch * out_stride + o] = y;
+        if (demod) {
+            const float cur = fast_arctan2_ref(y.y, y.x);
+            float prev;
+            if (o > 0) {
+                const float2 yp = total(o - 1);
+                prev = fast_arctan2_ref(yp.y, yp.x);
+            } else {
+                prev = demod_in[ch];
+            }
+            audio[ch * out_stride + o] = fm_step_ref(cur, prev, phasor_speed);
+            if (o == total_out - 1) demod_out[ch] = cur;
+        }
+    }
 }
 
 template <int Q, int DT, int NSEGT, bool ROT, bool DEMOD, bool SUPRED>
@@ -592,12 +659,15 @@ int launch_decim(DecimPlan* plan, const float2* hist, int H, const float2* in, c
     a.part = part.view;
     a.T = plan->T;
     a.D = plan->D;
+    a.DS = plan->DS;
+    a.nslices = plan->nslices;
     a.P = plan->P;
     a.NSEG = plan->NSEG;
     a.R = plan->R;
     a.NSTAGE = plan->NSTAGE;
     a.NSUP = plan->NSUP;
-    a.L = plan->NSUP * plan->Q - (plan->Q - 1) - lead;
+    const bool sliced = plan->nslices > 1;
+    a.L = plan->NSUP * plan->Q - (plan->Q - 1) - (sliced ? 0 : lead);
     a.nco = nco;
     a.abs0 = abs0;
     a.phasor_speed = phasor_speed;
@@ -607,10 +677,10 @@ int launch_decim(DecimPlan* plan, const float2* hist, int H, const float2* in, c
     a.audio = audio;
     a.out_stride = out_stride;
     const int per_tile = a.NSEG * a.L;
-    dim3 grid((part.max_out + per_tile - 1) / per_tile, part.view.nblocks, nch);
+    dim3 grid((part.max_out + per_tile - 1) / per_tile, part.view.nblocks, nch * plan->nslices);
     const size_t stage_bytes = (size_t)a.NSEG * (a.R * a.D + decim_seg_pad(a.D)) * sizeof(float2);
     const size_t smem_stage = (size_t)a.NSTAGE * stage_bytes + (size_t)2 * a.NSEG * a.R * (a.P | 1) * sizeof(float2) +
-                              (size_t)a.NSEG * (a.L + lead) * sizeof(float2) + 16 + a.NSTAGE * 8 + 64 +
+                              (size_t)a.NSEG * (a.L + 1) * sizeof(float2) + 16 + a.NSTAGE * 8 + 64 +
                               (a.P > 64 ? (size_t)2 * a.NSEG * a.R * 64 * sizeof(float2) : 0);
     const size_t smem_sup = (size_t)a.NSTAGE * stage_bytes + (size_t)2 * a.NSEG * plan->Q * decim_ppad_sup(a.P) * sizeof(float2) +
                             (size_t)a.NSEG * 4 * plan->Q * sizeof(float2) + 16 + a.NSTAGE * 8 + 64;
@@ -619,6 +689,43 @@ int launch_decim(DecimPlan* plan, const float2* hist, int H, const float2* in, c
         return -1;
     }
     const bool fused = mode == 1;
+    if (sliced) {
+        // partial outputs per (channel, slice) -> scratch, then the finish kernel sums them and demodulates
+        const size_t ystride = (size_t)((part.total_out + 63) / 64) * 64;
+        const size_t need = (size_t)nch * plan->nslices * ystride;
+        if (need > plan->ypart_cap) {
+            if (plan->ypart) cudaFree(plan->ypart);
+            plan->ypart = nullptr;
+            plan->ypart_cap = 0;
+            QDSP_CUDA_OK(cudaMalloc(&plan->ypart, need * sizeof(float2)));
+            plan->ypart_cap = need;
+        }
+        a.out_iq = plan->ypart;
+        a.audio = nullptr;
+        a.out_stride = (long long)ystride;
+        static const bool supred_s = getenv("QDSP_DECIM_SUPRED") ? atoi(getenv("QDSP_DECIM_SUPRED")) != 0 : true;
+        const bool sup = supred_s && plan->NT >= 2 * plan->NSEG * plan->Q;
+        const size_t sm = sup ? smem_sup : smem_stage;
+        int rc;
+        if (plan->Q == 9 && plan->D == 128 && plan->NSEG == 2 && sup)   // config 4: compile-time slice geometry
+            rc = fused ? launch_decim_t<9, 128, 2, true, false, true>(a, grid, plan->NT, sm, s)
+                       : launch_decim_t<9, 128, 2, false, false, true>(a, grid, plan->NT, sm, s);
+        else if (plan->Q == 9)
+            rc = fused ? (sup ? launch_decim_t<9, 0, 0, true, false, true>(a, grid, plan->NT, sm, s) : launch_decim_t<9, 0, 0, true, false, false>(a, grid, plan->NT, sm, s))
+                       : (sup ? launch_decim_t<9, 0, 0, false, false, true>(a, grid, plan->NT, sm, s) : launch_decim_t<9, 0, 0, false, false, false>(a, grid, plan->NT, sm, s));
+        else
+            rc = fused ? (sup ? launch_decim_t<6, 0, 0, true, false, true>(a, grid, plan->NT, sm, s) : launch_decim_t<6, 0, 0, true, false, false>(a, grid, plan->NT, sm, s))
+                       : (sup ? launch_decim_t<6, 0, 0, false, false, true>(a, grid, plan->NT, sm, s) : launch_decim_t<6, 0, 0, false, false, false>(a, grid, plan->NT, sm, s));
+        if (rc != 0) return rc;
+        long long gx = (part.total_out + 255) / 256;
+        if (gx > 1024) gx = 1024;
+        if (gx < 1) gx = 1;
+        decim_finish_kernel<<<dim3((unsigned)gx, nch), 256, 0, s>>>(plan->ypart, (long long)ystride, plan->nslices,
+                                                                     part.total_out, fused ? 1 : 0, phasor_speed, demod_in,
+                                                                     demod_out, out_iq, audio, out_stride);
+        QDSP_LAUNCH_OK();
+        return 0;
+    }
     static const bool supred_env = getenv("QDSP_DECIM_SUPRED") ? atoi(getenv("QDSP_DECIM_SUPRED")) != 0 : true;
     const bool supred = supred_env && plan->P <= 64 && plan->NT >= 2 * plan->NSEG * plan->Q;
     const size_t smem = supred ? smem_sup : smem_stage;
