@@ -73,6 +73,55 @@ namespace dsp {
         };
     }
 
+    // StereoFMDemod (reference demodulator.h:189-330): FloatFMDemod -> pilot FIR<float> -> AGC -> L/R matrix. The
+    // reference wires four threads through a Splitter; here one run() enqueues the four kernels back to back.
+    class StereoFMDemod : public generic_block<StereoFMDemod> {
+    public:
+        StereoFMDemod() {}
+        StereoFMDemod(stream<complex_t>* in, float sampleRate, float deviation) { init(in, sampleRate, deviation); }
+        ~StereoFMDemod() {
+            generic_block<StereoFMDemod>::stop();
+            if (h) { qdsp_stereofm_destroy(h); }
+        }
+        void init(stream<complex_t>* in, float sampleRate, float deviation) {
+            _in = in;
+            _sampleRate = sampleRate;
+            _deviation = deviation;
+            if (h) { qdsp_stereofm_destroy(h); }
+            h = qdsp_stereofm_create(_sampleRate, _deviation);
+            generic_block<StereoFMDemod>::registerInput(_in);
+            generic_block<StereoFMDemod>::registerOutput(&out);
+        }
+        void setInput(stream<complex_t>* in) {
+            std::lock_guard<std::mutex> lck(generic_block<StereoFMDemod>::ctrlMtx);
+            generic_block<StereoFMDemod>::tempStop();
+            generic_block<StereoFMDemod>::unregisterInput(_in);
+            _in = in;
+            generic_block<StereoFMDemod>::registerInput(_in);
+            generic_block<StereoFMDemod>::tempStart();
+        }
+        float getSampleRate() { return _sampleRate; }
+        float getDeviation() { return _deviation; }
+        int run() override {
+            const int count = _in->readDevice(cuStream);
+            if (count < 0) { return -1; }
+            out.acquireWriteDev(cuStream);
+            const int one = count;
+            const long long n = qdsp_stereofm_process(h, _in->readDev(), out.writeDev(), count, &one, 1, 0, cuStream);
+            _in->flushDevice(cuStream);
+            if (n < 0) { return -1; }
+            if (!out.swapDevice(count, cuStream)) { return -1; }
+            return count;
+        }
+
+        stream<stereo_t> out;
+
+    private:
+        float _sampleRate = 1, _deviation = 1;
+        stream<complex_t>* _in = nullptr;
+        qdsp_stereofm* h = nullptr;
+    };
+
     class FloatFMDemod : public detail::fm_demod_base<FloatFMDemod, float, 0> {
     public:
         FloatFMDemod() {}

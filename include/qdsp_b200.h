@@ -131,6 +131,18 @@ float qdsp_fmdemod_get_phase(qdsp_fmdemod* h);
 int qdsp_fmdemod_set_phase(qdsp_fmdemod* h, float phase);
 long long qdsp_fmdemod_process(qdsp_fmdemod* h, const void* in_dev, void* out_dev, long long count, qdsp_stream_t s);
 
+/* ---- StereoFMDemod::run, src/dsp/demodulator.h:189-330 ("next" row of the scope table) ------------------------ *
+ * FloatFMDemod -> pilot FIR<float>(BlackmanBandpassWindow(1000, 1000, 19000, fs)) -> AGC(20, fs) -> L/R matrix;   *
+ * out_dev is stereo_t[count]; the run() partition matters through the AGC.                                          */
+typedef struct qdsp_stereofm qdsp_stereofm;
+qdsp_stereofm* qdsp_stereofm_create(float sampleRate, float deviation);
+void qdsp_stereofm_destroy(qdsp_stereofm* h);
+long long qdsp_stereofm_process(qdsp_stereofm* h, const void* in_dev, void* out_dev, long long count, const int* blocks,
+                                int nblocks, int block_size, qdsp_stream_t s);
+/* the matrix step alone: out[i] = {mpx + mpx*pilot^2, mpx - mpx*pilot^2} */
+long long qdsp_stereo_matrix_process(const float* mpx_dev, const float* pilot_dev, void* out_dev, long long count,
+                                     qdsp_stream_t s);
+
 /* ---- fused VFO (vfo.h:19-36: Xlator(-offset) -> PolyphaseResampler) -> FloatFMDemod ---------- *
  * One pass: the translated and the resampled IQ never reach HBM unless iq_out_dev != NULL.        */
 typedef struct qdsp_vfofm qdsp_vfofm;

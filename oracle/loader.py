@@ -117,6 +117,8 @@ class Ref:
         L.ref_complex_agc.restype = _ll
         L.ref_ff_agc_cf32.argtypes = [_fp, _ip, _i, _fp, _ip, _ip]
         L.ref_ff_agc_cf32.restype = _ll
+        L.ref_stereo_fm.argtypes = [_f, _f, _fp, _ip, _i, _fp]
+        L.ref_stereo_fm.restype = _ll
         L.ref_costas.argtypes = [_i, _f, _fp, _ip, _i, _fp, _dp]
         L.ref_costas.restype = _ll
         L.ref_stream_buffer_size.restype = _i
@@ -247,6 +249,14 @@ class Ref:
         b = as_blocks(len(x), block)
         y = np.empty((len(x), 2), np.float32)
         n = self.lib.ref_fm_demod_stereo(fs, dev, px, _iptr(b), len(b), _fptr(y))
+        assert n == len(x)
+        return y
+
+    def stereo_fm(self, fs, dev, x, block):
+        x, px = self._cin(x)
+        b = as_blocks(len(x), block)
+        y = np.empty((len(x), 2), np.float32)
+        n = self.lib.ref_stereo_fm(fs, dev, px, _iptr(b), len(b), _fptr(y))
         assert n == len(x)
         return y
 
@@ -491,6 +501,16 @@ class Port:
         oc = np.zeros(len(b), np.int32)
         n = self.lib.port_power_decim(power, px, _iptr(b), len(b), _fptr(y.view(np.float32)), _iptr(oc))
         return y[:n].copy(), oc
+
+    def stereo_fm(self, fs, dev, x, block):
+        x, px = self._cin(x)
+        b = as_blocks(len(x), block)
+        y = np.empty((len(x), 2), np.float32)
+        self.lib.port_stereo_fm.argtypes = [_f, _f, _fp, _ip, _i, _fp]
+        self.lib.port_stereo_fm.restype = _ll
+        n = self.lib.port_stereo_fm(fs, dev, px, _iptr(b), len(b), _fptr(y))
+        assert n == len(x)
+        return y
 
     def fast_arctan2(self, y, x) -> float:
         return float(self.lib.port_fast_arctan2(y, x))

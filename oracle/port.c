@@ -412,6 +412,36 @@ long long port_vfo_fm(float offset, float inSR, float outSR, float bandWidth, fl
     return m;
 }
 
+void port_agc(float fallRate, float sampleRate, const float* x, const int* blocks, int nblocks, float* y, float* level_state);
+
+/* StereoFMDemod::run, src/dsp/demodulator.h:255-277, with its sub-blocks composed as init() wires them
+ * (:203-216): mpx = FloatFMDemod(x); pilot = AGC(20, fs)(FIR<float>(BlackmanBandpassWindow(1000, 1000, 19000, fs))(mpx));
+ * doubled = pilot*pilot; amb = mpx*doubled; out = {mpx + amb, mpx - amb}. Every sub-block sees the same run()
+ * partition. The pilot FIR's first-call history is uninitialised in the reference (filter.h:28): zeros here. */
+long long port_stereo_fm(float sampleRate, float deviation, const cf32* x, const int* blocks, int nblocks, float* out_lr) {
+    long long n = 0;
+    for (int b = 0; b < nblocks; b++) n += blocks[b];
+    float* mpx = (float*)malloc(sizeof(float) * (size_t)(n ? n : 1));
+    float* pil = (float*)malloc(sizeof(float) * (size_t)(n ? n : 1));
+    float* agc = (float*)malloc(sizeof(float) * (size_t)(n ? n : 1));
+    float ph = 0.0f;
+    port_fm_demod(x, n, port_fm_phasor_speed(sampleRate, deviation), &ph, mpx);
+    int T = port_blackman_tap_count(1000.0f, 1000.0f, sampleRate);
+    float* taps = (float*)malloc(sizeof(float) * (size_t)T);
+    port_blackman_bandpass_taps(1000.0f, 1000.0f, 19000.0f, sampleRate, taps, T, 1.0f);
+    port_fir_f32(taps, T, mpx, n, pil);
+    float level = 0.0f;
+    port_agc(20.0f, sampleRate, pil, blocks, nblocks, agc, &level);
+    for (long long i = 0; i < n; i++) {
+        float doubled = agc[i] * agc[i];   /* volk_32f_x2_multiply_32f */
+        float amb = mpx[i] * doubled;
+        out_lr[2 * i] = mpx[i] + amb;
+        out_lr[2 * i + 1] = mpx[i] - amb;
+    }
+    free(mpx); free(pil); free(agc); free(taps);
+    return n;
+}
+
 /* ------------------------------------------------------------------------------------------
  * Recurrent blocks
  * ---------------------------------------------------------------------------------------- */

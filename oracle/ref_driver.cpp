@@ -258,6 +258,18 @@ long long ref_fm_demod_stereo(float sampleRate, float deviation, const float* in
 }
 float ref_fast_arctan2(float y, float x) { return fast_arctan2(y, x); }
 
+// ---- StereoFMDemod: src/dsp/demodulator.h:189-330 (FloatFMDemod -> Splitter -> pilot FIR<float> with
+// BlackmanBandpassWindow(1000, 1000, 19000, fs) -> AGC(20, fs); L/R = mpx +- mpx * pilot^2) ---------------
+long long ref_stereo_fm(float sampleRate, float deviation, const float* in, const int* blocks, int nblocks,
+                        float* out) {
+    stream<complex_t> src;
+    StereoFMDemod d(&src, sampleRate, deviation);
+    d.start();
+    long long n = pump(&src, &d.out, (const complex_t*)in, blocks, nblocks, (stereo_t*)out, nullptr, nullptr);
+    d.stop();
+    return n;
+}
+
 // ---- the fused chain as the reference composes it: VFO -> FloatFMDemod (3 worker threads) ----
 long long ref_vfo_fm(float offset, float inSR, float outSR, float bandWidth, float deviation, const float* in,
                      const int* blocks, int nblocks, float* audio, int* out_counts, double* seconds) {

@@ -426,6 +426,21 @@ class FMDemod(FloatFMDemod):
     _stereo = 1
 
 
+class StereoFMDemod(_Block):
+    """dsp::StereoFMDemod: init(in, sampleRate, deviation) -> stereo_t (viewed as complex64: l = re, r = im)."""
+
+    _destroy = "qdsp_stereofm_destroy"
+
+    def __init__(self, sampleRate: float, deviation: float):
+        super().__init__()
+        _lib.require_device()
+        self.h = check(_L().qdsp_stereofm_create(float(sampleRate), float(deviation)), "qdsp_stereofm_create")
+
+    def _run(self, in_ptr, out_ptr, n, block):
+        b, nb, bs = _blocks_arg(n, block)
+        return _L().qdsp_stereofm_process(self.h, in_ptr, out_ptr, n, _iptr(b), nb, bs, self.stream)
+
+
 class VFO:
     """dsp::VFO (vfo.h): FrequencyXlator(-offset) -> PolyphaseResampler with the auto-designed window,
     run block by block as two kernels (the unfused composition; `VFOFM` is the fused pass)."""

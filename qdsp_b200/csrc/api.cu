@@ -917,6 +917,62 @@ float qdsp_costas_last_residual(qdsp_costas* h) {
 }
 
 // =================================================================================================
+// StereoFMDemod (hierarchical): FloatFMDemod -> FIR<float> pilot filter -> AGC -> matrix
+// =================================================================================================
+}  // extern "C"
+struct qdsp_stereofm {
+    qdsp_fmdemod* fm = nullptr;
+    qdsp_fir* fir = nullptr;
+    qdsp_agc* agc = nullptr;
+    Scratch scratch;   // mpx | pilot | agc'd pilot (3 x count floats)
+};
+extern "C" {
+
+qdsp_stereofm* qdsp_stereofm_create(float sampleRate, float deviation) {
+    qdsp_stereofm* h = new (std::nothrow) qdsp_stereofm();
+    if (!h) return nullptr;
+    h->fm = qdsp_fmdemod_create(sampleRate, deviation, 0);
+    // win.init(1000, 1000, 19000, sampleRate), demodulator.h:212
+    const int T = qdsp_blackman_tap_count(1000.0f, 1000.0f, sampleRate);
+    std::vector<float> taps(T);
+    qdsp_blackman_bandpass_taps(1000.0f, 1000.0f, 19000.0f, sampleRate, taps.data(), T, 1.0f);
+    h->fir = qdsp_fir_create(QDSP_F32, taps.data(), T);
+    h->agc = qdsp_agc_create(20.0f, sampleRate);   // agc.init(&filter.out, 20.0f, sampleRate), :214
+    if (!h->fm || !h->fir || !h->agc) {
+        qdsp_stereofm_destroy(h);
+        return nullptr;
+    }
+    return h;
+}
+void qdsp_stereofm_destroy(qdsp_stereofm* h) {
+    if (!h) return;
+    if (h->fm) qdsp_fmdemod_destroy(h->fm);
+    if (h->fir) qdsp_fir_destroy(h->fir);
+    if (h->agc) qdsp_agc_destroy(h->agc);
+    delete h;
+}
+long long qdsp_stereofm_process(qdsp_stereofm* h, const void* in_dev, void* out_dev, long long count, const int* blocks,
+                                int nblocks, int block_size, qdsp_stream_t s) {
+    if (count < 0) return -1;
+    if (count == 0) return 0;
+    if (h->scratch.reserve(sizeof(float) * 3 * (size_t)count + 256) != 0) return -1;
+    float* mpx = (float*)h->scratch.p;
+    float* pil = mpx + count;
+    float* lvl = pil + count;
+    if (qdsp_fmdemod_process(h->fm, in_dev, mpx, count, s) < 0) return -1;
+    if (qdsp_fir_process(h->fir, mpx, pil, count, s) < 0) return -1;
+    if (qdsp_agc_process(h->agc, pil, lvl, count, blocks, nblocks, block_size, s) < 0) return -1;
+    if (launch_stereo_matrix(mpx, lvl, (float2*)out_dev, count, as_stream(s)) != 0) return -1;
+    return count;
+}
+long long qdsp_stereo_matrix_process(const float* mpx_dev, const float* pilot_dev, void* out_dev, long long count,
+                                     qdsp_stream_t s) {
+    if (count < 0) return -1;
+    if (launch_stereo_matrix(mpx_dev, pilot_dev, (float2*)out_dev, count, as_stream(s)) != 0) return -1;
+    return count;
+}
+
+// =================================================================================================
 // synthetic IQ + probes
 // =================================================================================================
 int qdsp_synth_uniform_cf32(void* out_dev, unsigned long long seed, long long start, long long count,

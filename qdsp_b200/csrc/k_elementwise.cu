@@ -113,6 +113,24 @@ int launch_power_decim(const float2* in, float2* out, long long n_out, int copy_
     return 0;
 }
 
+// ---- StereoFMDemod's matrix step (reference demodulator.h:261-272): doubled = pilot*pilot; amb = mpx*doubled;
+// out = {mpx + amb, mpx - amb}, every product and sum rounded separately like the VOLK calls it replaces ----------
+__global__ void __launch_bounds__(256) stereo_matrix_kernel(const float* __restrict__ mpx, const float* __restrict__ pilot,
+                                                           float2* __restrict__ out, long long count) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += stride) {
+        const float m = mpx[i], p = pilot[i];
+        const float amb = __fmul_rn(m, __fmul_rn(p, p));
+        out[i] = make_float2(__fadd_rn(m, amb), __fsub_rn(m, amb));
+    }
+}
+int launch_stereo_matrix(const float* mpx, const float* pilot, float2* out, long long count, cudaStream_t s) {
+    if (count <= 0) return 0;
+    stereo_matrix_kernel<<<stream_grid(count, 256, 8), 256, 0, s>>>(mpx, pilot, out, count);
+    QDSP_LAUNCH_OK();
+    return 0;
+}
+
 // ---- synthetic IQ (integer recipe identical to qdsp_b200/synth.py) -------------------
 __device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
     z += 0x9E3779B97F4A7C15ull;

@@ -27,6 +27,7 @@ int launch_xlator(const float2* in, float2* out, long long count, uint64_t phase
                   float2 inc2, float2 inc3, cudaStream_t s);
 int launch_fmdemod(const float2* in, void* out, long long count, float phasor_speed, const float* state_in,
                    float* state_out, int stereo, cudaStream_t s);
+int launch_stereo_matrix(const float* mpx, const float* pilot, float2* out, long long count, cudaStream_t s);
 int launch_power_decim(const float2* in, float2* out, long long n_out, int copy_only, cudaStream_t s);
 int launch_synth_uniform(float2* out, unsigned long long seed, long long start, long long count, cudaStream_t s);
 int launch_synth_fm(float2* out, long long start, long long count, long long fs, long long fc, long long fm,

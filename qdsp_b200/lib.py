@@ -89,6 +89,10 @@ SIGNATURES = {
     "qdsp_fmdemod_get_phase": (_f, [_vp]),
     "qdsp_fmdemod_set_phase": (_i, [_vp, _f]),
     "qdsp_fmdemod_process": (_ll, [_vp, _vp, _vp, _ll, _vp]),
+    "qdsp_stereofm_create": (_vp, [_f, _f]),
+    "qdsp_stereofm_destroy": (None, [_vp]),
+    "qdsp_stereofm_process": (_ll, [_vp, _vp, _vp, _ll, _ip, _i, _i, _vp]),
+    "qdsp_stereo_matrix_process": (_ll, [_vp, _vp, _vp, _ll, _vp]),
     "qdsp_vfofm_create": (_vp, [_f, _f, _f, _f, _f]),
     "qdsp_vfofm_destroy": (None, [_vp]),
     "qdsp_vfofm_design": (_i, [_vp, _ip, _ip, _ip]),

@@ -93,3 +93,24 @@ def bpsk_cf32(seed: int, start: int, count: int, sps: int = 4, freq_off: float =
     const = 1.0 - 2.0 * (sym & np.uint64(1)).astype(np.float64)
     sig = const * np.exp(1j * freq_off * n.astype(np.float64))
     return sig.astype(np.complex64) + np.float32(sigma) * uniform_cf32(seed, start, count)
+
+
+def stereo_mpx_fm_cf32(start: int, count: int, fs: int = 240_000, dev: float = 75e3, fl: int = 700, fr: int = 1_100,
+                       amp: float = 0.8) -> np.ndarray:
+    """Broadcast-FM style baseband: stereo multiplex (L+R, 19 kHz pilot, (L-R) on 38 kHz DSB-SC) frequency-modulated
+    with peak deviation `dev` at sample rate `fs`. The phase integral is evaluated in closed form, so any window
+    of the stream can be generated independently."""
+    n = np.arange(start, start + count, dtype=np.int64)
+
+    def cosint(f, scale=1.0):   # integral of scale*sin(2*pi*f*t) dt, sampled at n/fs (closed form)
+        return -scale * np.cos(2.0 * np.pi * _frac(n, f, fs)) / (2.0 * np.pi * f)
+
+    # mpx = 0.45*(L+R) + 0.1*pilot + 0.45*(L-R)*sin(2*pi*38k t), L = sin(2*pi*fl t), R = sin(2*pi*fr t)
+    # products of sines expand into sum/difference tones, each integrated in closed form
+    integ = 0.45 * (cosint(fl) + cosint(fr)) + 0.1 * cosint(19_000)
+    for fa, sgn in ((fl, 1.0), (fr, -1.0)):
+        # sin(a) * sin(b) = 0.5*(cos(a-b) - cos(a+b)); integral of cos(2*pi*f t) = sin(2*pi*f t)/(2*pi*f)
+        for fb, s2 in ((38_000 - fa, 1.0), (38_000 + fa, -1.0)):
+            integ += sgn * 0.45 * 0.5 * s2 * np.sin(2.0 * np.pi * _frac(n, fb, fs)) / (2.0 * np.pi * fb)
+    ph = 2.0 * np.pi * dev * integ
+    return (amp * np.exp(1j * ph)).astype(np.complex64)

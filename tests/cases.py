@@ -18,11 +18,15 @@ CASES = {
     "rational_f32": dict(kind="resamp_f32", win=(3e3, 3e3, 48e3), in_sr=48e3, out_sr=44.1e3, src=("uniform_f32", 8, 0, 6000), block=[1470, 1471, 3059]),
     "interp": dict(kind="resamp", win=(10e3, 5e3, 48e3), in_sr=48e3, out_sr=192e3, src=("uniform", 9, 0, 3000), block=1000),
     "power_decim1": dict(kind="power_decim", power=1, src=("uniform", 12, 0, 4096), block=1024),
-    "power_decim3": dict(kind="power_decim", power=3, src=("uniform", 12, 0, 4096), block=1024),
+    # power > 1 re-reads the input buffer AFTER flush() (resampling.h:235-245): racy against the next swap in the
+    # reference, so the golden case is a single run() call
+    "power_decim3": dict(kind="power_decim", power=3, src=("uniform", 12, 0, 4096), block=4096),
     # NCO translator alone (float recursive phasor in the reference: short enough that drift is < 1e-5)
     "xlator": dict(kind="xlator", fs=FS, freq=-250e3, src=("uniform", 2, 0, 3000), block=[1000, 777, 1223]),
     "fm": dict(kind="fm", fs=48e3, dev=5e3, src=("fm48k", 0, 5000), block=[1024, 1, 3975]),
     "fm_stereo": dict(kind="fm_stereo", fs=48e3, dev=5e3, src=("fm48k", 0, 2000), block=1000),
+    # "next" row: the WFM stereo tail (FloatFMDemod -> pilot FIR<float> 961 taps -> AGC -> matrix) at 240 kS/s
+    "stereo_fm": dict(kind="stereo_fm", fs=240e3, dev=75e3, src=("stereo_mpx", 0, 12000), block=[5000, 3000, 4000]),
     # VFO alone and config 2's fused chain: 2.4 MS/s -> 48 kS/s (401 taps, I=1, D=50) + FloatFMDemod
     "vfo": dict(kind="vfo", offset=250e3, in_sr=FS, out_sr=48e3, bw=48e3, src=("cfg2", 0, 40000), block=10000),
     "vfo_fm": dict(kind="vfo_fm", offset=250e3, in_sr=FS, out_sr=48e3, bw=48e3, dev=5e3, src=("cfg2", 0, 81920), block=8192 * 5),
@@ -51,6 +55,8 @@ def make_input(c) -> np.ndarray:
         return synth.cfg2_input(src[1], src[2])
     if k == "fm48k":  # an FM signal already at 48 kS/s (demod-only cases)
         return synth.fm_cf32(src[1], src[2], 48_000, 3_000, 400, 5e3, 0.7) + np.float32(0.01) * synth.uniform_cf32(3, src[1], src[2])
+    if k == "stereo_mpx":
+        return synth.stereo_mpx_fm_cf32(src[1], src[2])
     if k == "cfg4mini":
         return synth.cfg4_input(src[1], src[2], nch=4, fs=6_144_000, spacing=240_000)
     if k == "qpsk":

@@ -36,6 +36,8 @@ def run_port(c, x):
     if k == "fm_stereo":
         y = P.fm_demod(c["fs"], c["dev"], x)
         return np.stack([y, y], axis=1), None
+    if k == "stereo_fm":
+        return P.stereo_fm(c["fs"], c["dev"], x, c["block"]), None
     if k == "vfo":
         a, oc, iq = P.vfo_fm(c["offset"], c["in_sr"], c["out_sr"], c["bw"], 5e3, x, c["block"], want_iq=True)
         return iq, oc
@@ -111,6 +113,9 @@ def run_gpu(c, x, variant=0):
         if k == "fm_stereo":
             y = y.view(np.float32).reshape(-1, 2)
         return y, None
+    if k == "stereo_fm":
+        y = B.StereoFMDemod(c["fs"], c["dev"]).process(x, c["block"])
+        return y.view(np.float32).reshape(-1, 2), None
     if k == "vfo":
         v = B.VFOFM(c["offset"], c["in_sr"], c["out_sr"], c["bw"], 5e3)
         v.set_variant(variant)

@@ -46,6 +46,7 @@ void wire(dsp::stream<dsp::complex_t>* in, dsp::stream<float>* fin, dsp::stream<
     dsp::VFO vfo(in, 250e3f, 2.4e6f, 48e3f, 48e3f);
     dsp::FloatFMDemod fm(vfo.out, 48e3f, 5e3f);
     dsp::FMDemod fms(vfo.out, 48e3f, 5e3f);
+    dsp::StereoFMDemod sfm(vfo.out, 240e3f, 75e3f);
     dsp::BFMDeemp de(&fms.out, 48e3f, 50e-6f);
     dsp::AGC agc(&fm.out, 20.0f, 48e3f);
     dsp::ComplexAGC cagc(in, 1.0f, 65535.0f, 1e-3f);

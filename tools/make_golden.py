@@ -63,6 +63,8 @@ def main():
             y = R.fm_demod(c["fs"], c["dev"], x, c["block"])
         elif k == "fm_stereo":
             y = R.fm_demod_stereo(c["fs"], c["dev"], x, c["block"])
+        elif k == "stereo_fm":
+            y = R.stereo_fm(c["fs"], c["dev"], x, c["block"])
         elif k == "vfo":
             y, oc = R.vfo(c["offset"], c["in_sr"], c["out_sr"], c["bw"], x, c["block"])
             gold[name + "_oc"] = oc
