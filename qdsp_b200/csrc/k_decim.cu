@@ -729,12 +729,6 @@ int launch_decim(DecimPlan* plan, const float2* hist, int H, const float2* in, c
     static const bool supred_env = getenv("QDSP_DECIM_SUPRED") ? atoi(getenv("QDSP_DECIM_SUPRED")) != 0 : true;
     const bool supred = supred_env && plan->P <= 64 && plan->NT >= 2 * plan->NSEG * plan->Q;
     const size_t smem = supred ? smem_sup : smem_stage;
-    if (plan->Q == 9 && plan->D == 50 && plan->NSEG == 12)   // config 2: 2.4 MS/s -> 48 kS/s, 401 taps
-        return fused ? (supred ? launch_decim_t<9, 50, 12, true, true, true>(a, grid, plan->NT, smem, s) : launch_decim_t<9, 50, 12, true, true, false>(a, grid, plan->NT, smem, s))
-                     : (supred ? launch_decim_t<9, 50, 12, false, false, true>(a, grid, plan->NT, smem, s) : launch_decim_t<9, 50, 12, false, false, false>(a, grid, plan->NT, smem, s));
-    if (plan->Q == 9 && plan->D == 50 && plan->NSEG == 6)
-        return fused ? (supred ? launch_decim_t<9, 50, 6, true, true, true>(a, grid, plan->NT, smem, s) : launch_decim_t<9, 50, 6, true, true, false>(a, grid, plan->NT, smem, s))
-                     : (supred ? launch_decim_t<9, 50, 6, false, false, true>(a, grid, plan->NT, smem, s) : launch_decim_t<9, 50, 6, false, false, false>(a, grid, plan->NT, smem, s));
     if (plan->Q == 9 && plan->D == 50 && plan->NSEG == 5)
         return fused ? (supred ? launch_decim_t<9, 50, 5, true, true, true>(a, grid, plan->NT, smem, s) : launch_decim_t<9, 50, 5, true, true, false>(a, grid, plan->NT, smem, s))
                      : (supred ? launch_decim_t<9, 50, 5, false, false, true>(a, grid, plan->NT, smem, s) : launch_decim_t<9, 50, 5, false, false, false>(a, grid, plan->NT, smem, s));
