@@ -82,12 +82,24 @@ fir_dense_kernel(VStream<float2> xs, long long count, const float2* __restrict__
     {
         float* sf = reinterpret_cast<float*>(sq);
         const int nsamp = 2 * npairs;
-        for (int e = t; e < nsamp; e += kFirThreads) {
-            const long long i = B + e;
-            const float2 v = (i < count) ? xs.at(i) : make_float2(0.f, 0.f);
-            const int q = e >> 1, h = e & 1;
-            sf[4 * q + h] = v.x;
-            sf[4 * q + 2 + h] = v.y;
+        // batches of 8 loads per thread in flight together (a one-at-a-time loop exposes the DRAM latency 8x)
+        for (int e0 = t; e0 < nsamp; e0 += 8 * kFirThreads) {
+            float2 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int e = e0 + j * kFirThreads;
+                const long long i = B + e;
+                v[j] = (e < nsamp && i < count) ? xs.at(i) : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int e = e0 + j * kFirThreads;
+                if (e < nsamp) {
+                    const int q = e >> 1, h = e & 1;
+                    sf[4 * q + h] = v[j].x;
+                    sf[4 * q + 2 + h] = v[j].y;
+                }
+            }
         }
     }
     __syncthreads();
@@ -197,13 +209,24 @@ fir_decim_kernel(VStream<float2> xs, long long count, long long n_out, const flo
     {
         float* sf = reinterpret_cast<float*>(sq);
         const int nsamp = 2 * npairs * D;                             // consecutive input samples of the tile
-        for (int e = t; e < nsamp; e += kFirThreads) {
-            const long long i = B + e;
-            const float2 v = (i < count) ? xs.at(i) : make_float2(0.f, 0.f);
-            const int r = e % D, m = e / D;                           // sub-stream, index within it
-            const int q = m >> 1, h = m & 1;
-            sf[((size_t)r * npairs + q) * 4 + h] = v.x;
-            sf[((size_t)r * npairs + q) * 4 + 2 + h] = v.y;
+        for (int e0 = t; e0 < nsamp; e0 += 8 * kFirThreads) {
+            float2 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int e = e0 + j * kFirThreads;
+                const long long i = B + e;
+                v[j] = (e < nsamp && i < count) ? xs.at(i) : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int e = e0 + j * kFirThreads;
+                if (e < nsamp) {
+                    const int r = e % D, m = e / D;                   // sub-stream, index within it
+                    const int q = m >> 1, h = m & 1;
+                    sf[((size_t)r * npairs + q) * 4 + h] = v[j].x;
+                    sf[((size_t)r * npairs + q) * 4 + 2 + h] = v[j].y;
+                }
+            }
         }
     }
     __syncthreads();
