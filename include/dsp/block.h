@@ -49,6 +49,16 @@ namespace dsp {
         friend BLOCK;
 
     protected:
+        // setInput() of every block: pause the worker, swap the registered input stream, resume
+        template <class S>
+        void rebindInput(S*& slot, S* in) {
+            std::lock_guard<std::mutex> lck(ctrlMtx);
+            tempStop();
+            unregisterInput(slot);
+            slot = in;
+            registerInput(slot);
+            tempStart();
+        }
         void registerInput(untyped_steam* s) { inputs.push_back(s); }
         void unregisterInput(untyped_steam* s) { inputs.erase(std::remove(inputs.begin(), inputs.end(), s), inputs.end()); }
         void registerOutput(untyped_steam* s) { outputs.push_back(s); }

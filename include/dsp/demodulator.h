@@ -92,14 +92,7 @@ namespace dsp {
             generic_block<StereoFMDemod>::registerInput(_in);
             generic_block<StereoFMDemod>::registerOutput(&out);
         }
-        void setInput(stream<complex_t>* in) {
-            std::lock_guard<std::mutex> lck(generic_block<StereoFMDemod>::ctrlMtx);
-            generic_block<StereoFMDemod>::tempStop();
-            generic_block<StereoFMDemod>::unregisterInput(_in);
-            _in = in;
-            generic_block<StereoFMDemod>::registerInput(_in);
-            generic_block<StereoFMDemod>::tempStart();
-        }
+        void setInput(stream<complex_t>* in) { generic_block<StereoFMDemod>::rebindInput(_in, in); }
         float getSampleRate() { return _sampleRate; }
         float getDeviation() { return _deviation; }
         int run() override {

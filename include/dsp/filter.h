@@ -26,14 +26,7 @@ namespace dsp {
             base::registerInput(_in);
             base::registerOutput(&out);
         }
-        void setInput(stream<T>* in) {
-            std::lock_guard<std::mutex> lck(base::ctrlMtx);
-            base::tempStop();
-            base::unregisterInput(_in);
-            _in = in;
-            base::registerInput(_in);
-            base::tempStart();
-        }
+        void setInput(stream<T>* in) { base::rebindInput(_in, in); }
         // the reference swaps taps without stopping the worker (filter.h:43-49, a race); here the worker is
         // paused so the new taps take effect between two run() calls
         void updateWindow(dsp::filter_window::generic_window* window) {
@@ -83,14 +76,7 @@ namespace dsp {
             generic_block<BFMDeemp>::registerInput(_in);
             generic_block<BFMDeemp>::registerOutput(&out);
         }
-        void setInput(stream<stereo_t>* in) {
-            std::lock_guard<std::mutex> lck(generic_block<BFMDeemp>::ctrlMtx);
-            generic_block<BFMDeemp>::tempStop();
-            generic_block<BFMDeemp>::unregisterInput(_in);
-            _in = in;
-            generic_block<BFMDeemp>::registerInput(_in);
-            generic_block<BFMDeemp>::tempStart();
-        }
+        void setInput(stream<stereo_t>* in) { generic_block<BFMDeemp>::rebindInput(_in, in); }
         void setSampleRate(float sampleRate) { _sampleRate = sampleRate; rebuild(); }
         void setTau(float tau) { _tau = tau; rebuild(); }
         int run() override {

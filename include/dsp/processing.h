@@ -29,14 +29,7 @@ namespace dsp {
         }
         // (sic) the reference names its setInput "setInputSize" (processing.h:26); both spellings work here
         void setInputSize(stream<complex_t>* in) { setInput(in); }
-        void setInput(stream<complex_t>* in) {
-            std::lock_guard<std::mutex> lck(base::ctrlMtx);
-            base::tempStop();
-            base::unregisterInput(_in);
-            _in = in;
-            base::registerInput(_in);
-            base::tempStart();
-        }
+        void setInput(stream<complex_t>* in) { base::rebindInput(_in, in); }
         void setSampleRate(float sampleRate) {
             _sampleRate = sampleRate;
             qdsp_xlator_set_frequency(h, _sampleRate, _freq);
@@ -82,14 +75,7 @@ namespace dsp {
             generic_block<AGC>::registerInput(_in);
             generic_block<AGC>::registerOutput(&out);
         }
-        void setInput(stream<float>* in) {
-            std::lock_guard<std::mutex> lck(generic_block<AGC>::ctrlMtx);
-            generic_block<AGC>::tempStop();
-            generic_block<AGC>::unregisterInput(_in);
-            _in = in;
-            generic_block<AGC>::registerInput(_in);
-            generic_block<AGC>::tempStart();
-        }
+        void setInput(stream<float>* in) { generic_block<AGC>::rebindInput(_in, in); }
         void setSampleRate(float sampleRate) {
             std::lock_guard<std::mutex> lck(generic_block<AGC>::ctrlMtx);
             _sampleRate = sampleRate;
@@ -143,14 +129,7 @@ namespace dsp {
             base::registerInput(_in);
             base::registerOutput(&out);
         }
-        void setInput(stream<T>* in) {
-            std::lock_guard<std::mutex> lck(base::ctrlMtx);
-            base::tempStop();
-            base::unregisterInput(_in);
-            _in = in;
-            base::registerInput(_in);
-            base::tempStart();
-        }
+        void setInput(stream<T>* in) { base::rebindInput(_in, in); }
         // emits the valid (toProcess) outputs; the reference swaps `count` elements of which only toProcess are
         // fresh (processing.h:221) -- consumers here see exactly the fresh ones
         int run() override {
@@ -189,14 +168,7 @@ namespace dsp {
             generic_block<ComplexAGC>::registerInput(_in);
             generic_block<ComplexAGC>::registerOutput(&out);
         }
-        void setInput(stream<complex_t>* in) {
-            std::lock_guard<std::mutex> lck(generic_block<ComplexAGC>::ctrlMtx);
-            generic_block<ComplexAGC>::tempStop();
-            generic_block<ComplexAGC>::unregisterInput(_in);
-            _in = in;
-            generic_block<ComplexAGC>::registerInput(_in);
-            generic_block<ComplexAGC>::tempStart();
-        }
+        void setInput(stream<complex_t>* in) { generic_block<ComplexAGC>::rebindInput(_in, in); }
         void setSetPoint(float setPoint) { _setPoint = setPoint; rebuild(); }
         void setMaxGain(float maxGain) { _maxGain = maxGain; rebuild(); }
         void setRate(float rate) { _rate = rate; rebuild(); }

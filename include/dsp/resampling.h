@@ -31,14 +31,7 @@ namespace dsp {
             base::registerInput(_in);
             base::registerOutput(&out);
         }
-        void setInput(stream<T>* in) {
-            std::lock_guard<std::mutex> lck(base::ctrlMtx);
-            base::tempStop();
-            base::unregisterInput(_in);
-            _in = in;
-            base::registerInput(_in);
-            base::tempStart();
-        }
+        void setInput(stream<T>* in) { base::rebindInput(_in, in); }
         // like the reference (resampling.h:53-73) the rate setters recompute I/D but keep the current taps
         // until updateWindow() is called
         void setInSampleRate(float inSampleRate) {
@@ -107,14 +100,7 @@ namespace dsp {
             generic_block<PowerDecimator>::registerInput(_in);
             generic_block<PowerDecimator>::registerOutput(&out);
         }
-        void setInput(stream<complex_t>* in) {
-            std::lock_guard<std::mutex> lck(generic_block<PowerDecimator>::ctrlMtx);
-            generic_block<PowerDecimator>::tempStop();
-            generic_block<PowerDecimator>::unregisterInput(_in);
-            _in = in;
-            generic_block<PowerDecimator>::registerInput(_in);
-            generic_block<PowerDecimator>::tempStart();
-        }
+        void setInput(stream<complex_t>* in) { generic_block<PowerDecimator>::rebindInput(_in, in); }
         void setPower(unsigned int power) {
             std::lock_guard<std::mutex> lck(generic_block<PowerDecimator>::ctrlMtx);
             generic_block<PowerDecimator>::tempStop();

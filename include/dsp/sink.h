@@ -19,14 +19,7 @@ namespace dsp {
             _ctx = ctx;
             base::registerInput(_in);
         }
-        void setInput(stream<T>* in) {
-            std::lock_guard<std::mutex> lck(base::ctrlMtx);
-            base::tempStop();
-            base::unregisterInput(_in);
-            _in = in;
-            base::registerInput(_in);
-            base::tempStart();
-        }
+        void setInput(stream<T>* in) { base::rebindInput(_in, in); }
         void setHandler(void (*handler)(T* data, int count, void* ctx), void* ctx) {
             std::lock_guard<std::mutex> lck(base::ctrlMtx);
             base::tempStop();
