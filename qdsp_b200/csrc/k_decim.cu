@@ -521,6 +521,298 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
     epilogue(nsup - 1);
 }
 
+// ---- v2: one stage per super-iteration ------------------------------------------------------------
+// Same column-pair formulation, but a ring slot holds a whole super-iteration (Q rows per segment) and the ring is
+// a double buffer: ONE CTA barrier per Q rows publishes the column partials and releases the slot (v1 needs one
+// per 3 rows), so the per-stage bookkeeping (mbarrier wait, producer, reduce/epilogue dispatch) is amortised over
+// 3x more samples. The 2-lane reduce also evaluates fast_arctan2 once per output and parks the angle, so the FM
+// epilogue is a subtraction. Compile-time geometry only (D, NSEG); 128-thread CTAs, 4 per SM.
+template <int Q, int D, int NSEG>
+struct SupGeom {
+    static constexpr int P = D / 2;
+    static constexpr int NSLOT = 2;
+    static constexpr int chunk_elems = Q * D;
+    static constexpr uint32_t chunk_bytes = (uint32_t)chunk_elems * 8u;
+    static constexpr int seg_pad = ((((D * 8) % 128) - (int)(chunk_bytes % 128u)) % 128 + 128) % 128 / 8;
+    static constexpr int seg_pitch = chunk_elems + seg_pad;
+    static constexpr uint32_t stage_bytes = (uint32_t)NSEG * (uint32_t)seg_pitch * 8u;
+    static constexpr int Ppad = P + ((2 - (P & 3)) & 3);          // == 2 (mod 4): see decim_ppad_sup
+    static constexpr uint32_t pbuf_half = (uint32_t)(NSEG * Q * Ppad) * 8u;
+    static constexpr int RY = 4 * Q;                              // parked outputs / angles per segment (ring)
+    static constexpr size_t off_pbuf = (size_t)NSLOT * stage_bytes;
+    static constexpr size_t off_ybuf = off_pbuf + 2 * (size_t)pbuf_half;
+    static constexpr size_t off_abuf = off_ybuf + (size_t)NSEG * RY * 8;
+    static constexpr size_t off_mbar = (off_abuf + (size_t)NSEG * RY * 4 + 7) / 8 * 8;
+    static constexpr size_t off_misc = off_mbar + NSLOT * 8;
+    static constexpr size_t smem_bytes = off_misc + 16;
+};
+
+template <int Q, int DT, int NSEGT, bool ROT, bool DEMOD>
+__global__ void __launch_bounds__(128, 4) decim_sup_kernel(const DecimArgs a) {
+    using G = SupGeom<Q, DT, NSEGT>;
+    constexpr int D = DT, NSEG = NSEGT, P = G::P, NT = 128;
+    constexpr int LEAD = DEMOD ? 1 : 0;
+    constexpr int RY = G::RY;
+    static_assert(NSEG * P <= NT && 2 * NSEG * Q <= NT, "CTA geometry");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int L = a.L;
+    const int t = threadIdx.x;
+    const int b = blockIdx.y;
+    const int ch = blockIdx.z / a.nslices, slice = blockIdx.z - ch * a.nslices;
+    const int plane = blockIdx.z;
+    const int DSg = a.DS;
+    const long long col_off = (long long)slice * D;
+    const BlkInfo bi = a.part.get(b);
+    const int k0 = blockIdx.x * (NSEG * L);
+    if (k0 >= bi.out_count) return;
+
+    const long long chunk_span = (long long)Q * DSg;               // global samples one stage advances
+    const long long chunk_tail = (long long)(Q - 1) * DSg + D;     // from a chunk's first sample to past its last
+    const int LOUT = L + LEAD;
+    float2* X = reinterpret_cast<float2*>(smem_raw);
+    float2* Pbuf = reinterpret_cast<float2*>(smem_raw + G::off_pbuf);   // [2][NSEG*Q][Ppad]
+    float2* ybuf = reinterpret_cast<float2*>(smem_raw + G::off_ybuf);   // [NSEG][RY]
+    float* abuf = reinterpret_cast<float*>(smem_raw + G::off_abuf);     // [NSEG][RY] angles of the parked outputs
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + G::off_mbar);
+    float* s_misc = reinterpret_cast<float*>(smem_raw + G::off_misc);
+
+    const int seg = t / P;
+    const int pair = t - seg * P;
+    const bool in_grid = seg < NSEG;
+    const int pad = (int)((bi.in_start - a.T) & 1);
+    const int ks = k0 + seg * L - LEAD;
+    const long long seg_base = bi.in_start + (long long)ks * DSg - a.T - pad + col_off;
+    const bool seg_active = in_grid && (k0 + seg * L < bi.out_count);
+    const int need = (bi.out_count - k0 < L ? bi.out_count - k0 : L) + LEAD + Q - 1;
+    const int nsup = (need + Q - 1) / Q < a.NSUP ? (need + Q - 1) / Q : a.NSUP;
+    int fast_lo = 0, fast_hi = 0, live_hi = 0;
+    if (seg_active) {
+        live_hi = nsup;
+        const long long lo = seg_base >= 0 ? 0 : (-seg_base + chunk_span - 1) / chunk_span;
+        const long long room = a.n_in - seg_base - chunk_tail;
+        const long long hi = room < 0 ? 0 : room / chunk_span + 1;
+        fast_lo = (int)(lo < nsup ? lo : nsup);
+        fast_hi = (int)(hi < nsup ? hi : nsup);
+    }
+
+    uint64_t nco_step = 0, nco_ph0 = 0;
+    if (ROT) {
+        nco_step = a.nco[ch].step;
+        nco_ph0 = a.nco[ch].init + nco_step * (uint64_t)a.abs0;
+    }
+    if (t == 0) {
+        for (int s = 0; s < G::NSLOT; s++) mbar_init(&mbar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    bool use_override = false;
+    if (DEMOD && blockIdx.x == 0) {
+        int pb = b - 1;
+        BlkInfo pbi{};
+        while (pb >= 0) {
+            pbi = a.part.get(pb);
+            if (pbi.out_count > 0) break;
+            pb--;
+        }
+        if (pb < 0) {
+            use_override = true;
+            if (t == 0) s_misc[0] = a.demod_in[ch];
+        } else if (pb != b - 1 || pbi.in_start + (long long)pbi.out_count * DSg != bi.in_start) {
+            use_override = true;
+            if (t < 32) {
+                const float2 y = direct_output_warp<ROT>(
+                    a, pbi.in_start + (long long)(pbi.out_count - 1) * DSg - a.T, nco_ph0, nco_step);
+                if (t == 0) s_misc[0] = fast_arctan2_ref(y.y, y.x);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- producer: warp 0, lane l issues segment l's bulk copy (Q rows) ------------------------------
+    float2* xseg = X + (size_t)seg * G::seg_pitch;
+    const int nactive = (bi.out_count - k0 + L - 1) / L < NSEG ? (bi.out_count - k0 + L - 1) / L : NSEG;
+    const long long tile_first = bi.in_start + (long long)(k0 - LEAD) * DSg - a.T - pad + col_off;
+    const long long tile_last = tile_first + (long long)(nactive - 1) * L * DSg + (long long)(nsup - 1) * chunk_span + chunk_tail;
+    const bool edge_tile = tile_first < 0 || tile_last > a.n_in;
+    const float2* p_gsrc = nullptr;
+    int p_lo = 0, p_hi = 0;
+    unsigned char* p_dst = nullptr;
+    if (t < 32 && t < nactive) {
+        const long long pbase = tile_first + (long long)t * L * DSg;
+        const long long lo = pbase >= 0 ? 0 : (-pbase + chunk_span - 1) / chunk_span;
+        const long long room = a.n_in - pbase - chunk_tail;
+        const long long hi = room < 0 ? 0 : room / chunk_span + 1;
+        p_lo = (int)(lo < nsup ? lo : nsup);
+        p_hi = (int)(hi < nsup ? hi : nsup);
+        p_gsrc = a.in + pbase;
+        p_dst = reinterpret_cast<unsigned char*>(X + (size_t)t * G::seg_pitch);
+    }
+    auto issue = [&](int it, int slot) {
+        if (t < 32) {
+            const bool fast = it >= p_lo && it < p_hi;
+            const unsigned m = __ballot_sync(0xffffffffu, fast);
+            if (t == 0) mbar_arrive_expect_tx(&mbar[slot], (uint32_t)__popc(m) * G::chunk_bytes);
+            __syncwarp();
+            if (fast) {
+                if (DSg == D) {
+                    tma_bulk_g2s(p_dst + slot * G::stage_bytes, p_gsrc + (size_t)it * G::chunk_elems, G::chunk_bytes, &mbar[slot]);
+                } else {   // sliced rows: one bulk copy per row
+#pragma unroll 1
+                    for (int rr = 0; rr < Q; rr++)
+                        tma_bulk_g2s(p_dst + slot * G::stage_bytes + (size_t)rr * D * 8, p_gsrc + ((size_t)it * Q + rr) * DSg,
+                                     (uint32_t)D * 8u, &mbar[slot]);
+                }
+            }
+        }
+        if (edge_tile && in_grid) {
+            const bool fast = it >= fast_lo && it < fast_hi;
+            if (!fast && it < live_hi) {
+                VStream<float2> xs{a.hist, a.in, a.H};
+                float2* dst = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(xseg) + slot * G::stage_bytes);
+                const long long start = seg_base + (long long)it * chunk_span;
+                for (int e = pair; e < G::chunk_elems; e += P) {
+                    const int rr = e / D;
+                    const long long i = start + (long long)rr * DSg + (e - rr * D);
+                    dst[e] = (i < a.n_in) ? xs.at(i) : make_float2(0.f, 0.f);
+                }
+            }
+        }
+    };
+
+    float2 tp[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) tp[q] = make_float2(0.f, 0.f);
+    if (in_grid) {
+        const float2* tt = a.taps + ((size_t)slice * 2 + pad) * Q * P;
+#pragma unroll
+        for (int q = 0; q < Q; q++) tp[q] = tt[q * P + pair];
+    }
+    float2 PR = make_float2(1.f, 1.f), PI = make_float2(0.f, 0.f);
+    float2 wr2 = make_float2(1.f, 1.f), wi2 = make_float2(0.f, 0.f);
+    const long long col0 = seg_base + 2 * pair;
+    if (ROT) {
+        const float2 w = phasor_from_turns(nco_step * (uint64_t)DSg);
+        wr2 = make_float2(w.x, w.x);
+        wi2 = make_float2(w.y, w.y);
+    }
+    float2 accRe[Q], accIm[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) accRe[q] = accIm[q] = make_float2(0.f, 0.f);
+
+    const unsigned char* xme = reinterpret_cast<const unsigned char*>(reinterpret_cast<const float4*>(xseg) + pair);
+    unsigned char* pme = reinterpret_cast<unsigned char*>(Pbuf + (seg * Q) * G::Ppad + pair);
+    constexpr uint32_t row_bytes = (uint32_t)D * 8u;
+    constexpr uint32_t prow_bytes = (uint32_t)G::Ppad * 8u;
+
+    issue(0, 0);
+    issue(1, 1);
+    __syncthreads();
+
+    // all NSEG*Q outputs of super-iteration `sup`: 2 lanes per output (packed adds); the even lane parks y and,
+    // for the FM epilogue, its angle
+    const int o2 = t >> 1, u2 = t & 1;
+    const bool v2 = o2 < NSEG * Q;
+    const int s2 = o2 / Q, i2 = o2 - s2 * Q;
+    const bool s2_live = v2 && u2 == 0 && (k0 + s2 * L < bi.out_count);
+    auto reduce_super = [&](int sup, int par) {
+        float2 sacc = make_float2(0.f, 0.f);
+        if (v2) {
+            const float2* pb = reinterpret_cast<const float2*>(reinterpret_cast<const unsigned char*>(Pbuf) + par * G::pbuf_half) + o2 * G::Ppad;
+            constexpr int NP2 = (P + 1) / 2;
+#pragma unroll
+            for (int i = 0; i < NP2; i++)
+                if (u2 + 2 * i < P) sacc = __fadd2_rn(sacc, pb[u2 + 2 * i]);
+        }
+        sacc.x += __shfl_xor_sync(0xffffffffu, sacc.x, 1);
+        sacc.y += __shfl_xor_sync(0xffffffffu, sacc.y, 1);
+        const int j = sup * Q + i2 - (Q - 1);
+        if (s2_live && j >= 0 && j < LOUT) {
+            const int slot = s2 * RY + (j % RY);
+            ybuf[slot] = sacc;
+            if (DEMOD) abuf[slot] = fast_arctan2_ref(sacc.y, sacc.x);
+        }
+    };
+    // epilogue of a finished super-iteration: one thread per output, taken from the top of the CTA (the low warps
+    // carry the producer and most of the reduce)
+    const int et = NT - 1 - t;
+    const int es = et / Q, er = et - es * Q;
+    auto epilogue = [&](int sup) {
+        if (et >= NSEG * Q) return;
+        const int j = sup * Q + er - (Q - 1);
+        const int k = k0 + es * L - LEAD + j;
+        if (j < LEAD || j >= LOUT || k >= bi.out_count) return;
+        const long long oidx = plane * a.out_stride + bi.out_start + k;
+        if (DEMOD) {
+            const float cur = abuf[es * RY + (j % RY)];
+            const float prev = (use_override && es == 0 && j == 1) ? s_misc[0] : abuf[es * RY + ((j - 1) % RY)];
+            a.audio[oidx] = fm_step_ref(cur, prev, a.phasor_speed);
+            if (bi.out_start + k == a.part.total_out - 1) a.demod_out[ch] = cur;
+            if (a.out_iq) a.out_iq[oidx] = ybuf[es * RY + (j % RY)];
+        } else {
+            a.out_iq[oidx] = ybuf[es * RY + (j % RY)];
+        }
+    };
+
+#pragma unroll 1
+    for (int sup2 = 0; sup2 < nsup; sup2 += 2) {
+        if (ROT && (sup2 & 7) == 0 && seg_active) {
+            const long long i0 = col0 + (long long)sup2 * Q * DSg;
+            const float2 p0 = phasor_from_turns(nco_ph0 + nco_step * (uint64_t)i0);
+            const float2 p1 = phasor_from_turns(nco_ph0 + nco_step * (uint64_t)(i0 + 1));
+            PR = make_float2(p0.x, p1.x);
+            PI = make_float2(p0.y, p1.y);
+        }
+        const uint32_t parity = (uint32_t)((sup2 >> 1) & 1);
+#pragma unroll
+        for (int slot = 0; slot < 2; slot++) {
+            const int sup = sup2 + slot;
+            if (sup < nsup) {
+                mbar_wait(&mbar[slot], parity);
+                if (seg_active) {
+                    const unsigned char* xs_ = xme + slot * G::stage_bytes;
+                    unsigned char* ps_ = pme + slot * G::pbuf_half;
+#pragma unroll
+                    for (int i = 0; i < Q; i++) {
+                        const float4 v = *reinterpret_cast<const float4*>(xs_ + i * row_bytes);
+                        float2 RE, IM;
+                        if (ROT) {
+                            RE.x = fmaf(v.x, PR.x, -(v.y * PI.x));
+                            IM.x = fmaf(v.x, PI.x, v.y * PR.x);
+                            RE.y = fmaf(v.z, PR.y, -(v.w * PI.y));
+                            IM.y = fmaf(v.z, PI.y, v.w * PR.y);
+                            const float2 nPR = __ffma2_rn(PI, neg2(wi2), __fmul2_rn(PR, wr2));
+                            PI = __ffma2_rn(PI, wr2, __fmul2_rn(PR, wi2));
+                            PR = nPR;
+                        } else {
+                            RE = make_float2(v.x, v.z);
+                            IM = make_float2(v.y, v.w);
+                        }
+#pragma unroll
+                        for (int q = 0; q < Q; q++) {
+                            const int sl = (i - q + Q) % Q;
+                            if (q == 0) {
+                                accRe[sl] = __fmul2_rn(RE, tp[0]);
+                                accIm[sl] = __fmul2_rn(IM, tp[0]);
+                            } else {
+                                accRe[sl] = __ffma2_rn(RE, tp[q], accRe[sl]);
+                                accIm[sl] = __ffma2_rn(IM, tp[q], accIm[sl]);
+                            }
+                        }
+                        const int e = (i + 1) % Q;
+                        *reinterpret_cast<float2*>(ps_ + i * prow_bytes) =
+                            make_float2(accRe[e].x + accRe[e].y, accIm[e].x + accIm[e].y);
+                    }
+                }
+                __syncthreads();              // slot consumed, this super-iteration's partials visible
+                issue(sup + 2, slot);         // refill the slot just drained
+                reduce_super(sup, slot);
+                if (sup > 0) epilogue(sup - 1);
+            }
+        }
+    }
+    __syncthreads();
+    epilogue(nsup - 1);
+}
+
 // ---- host side -------------------------------------------------------------------------------------
 bool decim_plan_supported(int T, int interp, int decim) {
     if (interp != 1 || (decim & 1) || decim < 8) return false;
@@ -641,6 +933,20 @@ static int launch_decim_t(const DecimArgs& a, dim3 grid, int NT, size_t smem, cu
     return 0;
 }
 
+template <int Q, int DT, int NSEGT, bool ROT, bool DEMOD>
+static int launch_decim_sup_t(const DecimArgs& a, dim3 grid, cudaStream_t s) {
+    auto kern = decim_sup_kernel<Q, DT, NSEGT, ROT, DEMOD>;
+    constexpr size_t smem = SupGeom<Q, DT, NSEGT>::smem_bytes;
+    QDSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 128, smem, s>>>(a);
+    QDSP_LAUNCH_OK();
+    return 0;
+}
+static bool decim_v2_enabled() {
+    static const bool on = getenv("QDSP_DECIM_V2") ? atoi(getenv("QDSP_DECIM_V2")) != 0 : true;
+    return on;
+}
+
 int launch_decim(DecimPlan* plan, const float2* hist, int H, const float2* in, const Partition& part, int mode,
                  const NcoDev* nco, long long abs0, int nch, float phasor_speed, const float* demod_in,
                  float* demod_out, float2* out_iq, float* audio, long long out_stride, cudaStream_t s) {
@@ -707,7 +1013,9 @@ int launch_decim(DecimPlan* plan, const float2* hist, int H, const float2* in, c
         const bool sup = supred_s && plan->NT >= 2 * plan->NSEG * plan->Q;
         const size_t sm = sup ? smem_sup : smem_stage;
         int rc;
-        if (plan->Q == 9 && plan->D == 128 && plan->NSEG == 2 && sup)   // config 4: compile-time slice geometry
+        if (plan->Q == 9 && plan->D == 128 && plan->NSEG == 2 && sup && plan->NT == 128 && decim_v2_enabled())
+            rc = fused ? launch_decim_sup_t<9, 128, 2, true, false>(a, grid, s) : launch_decim_sup_t<9, 128, 2, false, false>(a, grid, s);
+        else if (plan->Q == 9 && plan->D == 128 && plan->NSEG == 2 && sup)   // config 4: compile-time slice geometry
             rc = fused ? launch_decim_t<9, 128, 2, true, false, true>(a, grid, plan->NT, sm, s)
                        : launch_decim_t<9, 128, 2, false, false, true>(a, grid, plan->NT, sm, s);
         else if (plan->Q == 9)
@@ -729,6 +1037,8 @@ int launch_decim(DecimPlan* plan, const float2* hist, int H, const float2* in, c
     static const bool supred_env = getenv("QDSP_DECIM_SUPRED") ? atoi(getenv("QDSP_DECIM_SUPRED")) != 0 : true;
     const bool supred = supred_env && plan->P <= 64 && plan->NT >= 2 * plan->NSEG * plan->Q;
     const size_t smem = supred ? smem_sup : smem_stage;
+    if (plan->Q == 9 && plan->D == 50 && plan->NSEG == 5 && supred && plan->NT == 128 && decim_v2_enabled())
+        return fused ? launch_decim_sup_t<9, 50, 5, true, true>(a, grid, s) : launch_decim_sup_t<9, 50, 5, false, false>(a, grid, s);
     if (plan->Q == 9 && plan->D == 50 && plan->NSEG == 5)
         return fused ? (supred ? launch_decim_t<9, 50, 5, true, true, true>(a, grid, plan->NT, smem, s) : launch_decim_t<9, 50, 5, true, true, false>(a, grid, plan->NT, smem, s))
                      : (supred ? launch_decim_t<9, 50, 5, false, false, true>(a, grid, plan->NT, smem, s) : launch_decim_t<9, 50, 5, false, false, false>(a, grid, plan->NT, smem, s));
