@@ -521,42 +521,55 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
     epilogue(nsup - 1);
 }
 
-// ---- v2: one stage per super-iteration ------------------------------------------------------------
-// Same column-pair formulation, but a ring slot holds a whole super-iteration (Q rows per segment) and the ring is
-// a double buffer: ONE CTA barrier per Q rows publishes the column partials and releases the slot (v1 needs one
-// per 3 rows), so the per-stage bookkeeping (mbarrier wait, producer, reduce/epilogue dispatch) is amortised over
-// 3x more samples. The 2-lane reduce also evaluates fast_arctan2 once per output and parks the angle, so the FM
-// epilogue is a subtraction. Compile-time geometry only (D, NSEG); 128-thread CTAs, 4 per SM.
-template <int Q, int D, int NSEG>
+// ---- v2: one stage per super-iteration, dedicated producer/finisher warp ---------------------------
+// Same column-pair formulation as decim_kernel above, restructured around what its profiles showed:
+//  * a ring slot holds a whole super-iteration (Q rows per segment): ONE CTA barrier per Q rows publishes the
+//    column partials and releases the slot (v1 needs one per 3 rows), and the 9 row loads of a stage are scheduled
+//    ahead of the FFMA2 stream;
+//  * warps 0-3 only run the FIR main body; a fifth warp owns everything with a long dependent chain: it arms the
+//    mbarriers and issues the TMA bulk copies (double-buffered ring: one stage in flight while one is consumed), and
+//    it finishes the NSEG*Q outputs of super-iteration s while the compute warps are already in s+1 -- one lane per
+//    output: sum the P column partials (128-bit shared loads), fast_arctan2, previous angle from the neighbouring
+//    lane, fm step, store. Nothing of that sits between a compute warp and its next row any more.
+// Measured alternatives (config 2, same box, GS/s): finishing pass on two of the four compute warps 608; this
+// layout 640; the same with mbarrier hand-overs instead of the CTA barrier 618; two aux warps at 80 registers 601;
+// a 6-slot ring of 3-row stages (more bytes in flight, but a wait in front of every third row) 465; a 3-slot ring at
+// 3 CTAs/SM 585. Without the finishing pass the kernel runs at 725 (the data-movement ceiling of this layout is
+// 715-745), i.e. what is left is the aux warp's latency chain and one stage of prefetch depth.
+// Compile-time geometry only (D, NSEG); 160-thread CTAs, 4 per SM.
+template <int Q, int D, int NSEG, int NSLOTT = 2>
 struct SupGeom {
     static constexpr int P = D / 2;
-    static constexpr int NSLOT = 2;
+    static constexpr int NSLOT = NSLOTT;
     static constexpr int chunk_elems = Q * D;
     static constexpr uint32_t chunk_bytes = (uint32_t)chunk_elems * 8u;
     static constexpr int seg_pad = ((((D * 8) % 128) - (int)(chunk_bytes % 128u)) % 128 + 128) % 128 / 8;
     static constexpr int seg_pitch = chunk_elems + seg_pad;
     static constexpr uint32_t stage_bytes = (uint32_t)NSEG * (uint32_t)seg_pitch * 8u;
-    static constexpr int Ppad = P + ((2 - (P & 3)) & 3);          // == 2 (mod 4): see decim_ppad_sup
+    static constexpr int Ppad = P + ((2 - (P & 3)) & 3);          // even (16-byte rows), == 2 (mod 4)
     static constexpr uint32_t pbuf_half = (uint32_t)(NSEG * Q * Ppad) * 8u;
-    static constexpr int RY = 4 * Q;                              // parked outputs / angles per segment (ring)
+    static constexpr int SA = 32 / Q;                             // segments the finisher covers per pass
+    static constexpr int NPASS = (NSEG + SA - 1) / SA;
     static constexpr size_t off_pbuf = (size_t)NSLOT * stage_bytes;
-    static constexpr size_t off_ybuf = off_pbuf + 2 * (size_t)pbuf_half;
-    static constexpr size_t off_abuf = off_ybuf + (size_t)NSEG * RY * 8;
-    static constexpr size_t off_mbar = (off_abuf + (size_t)NSEG * RY * 4 + 7) / 8 * 8;
-    static constexpr size_t off_misc = off_mbar + NSLOT * 8;
+    static constexpr size_t off_mbar = (off_pbuf + 2 * (size_t)pbuf_half + 7) / 8 * 8;
+    static constexpr size_t off_misc = off_mbar + NSLOT * 8;      // [0] override angle
     static constexpr size_t smem_bytes = off_misc + 16;
+    static_assert(off_pbuf % 16 == 0 && (Ppad * 8) % 16 == 0 && pbuf_half % 16 == 0, "128-bit partial loads");
 };
 
-template <int Q, int DT, int NSEGT, bool ROT, bool DEMOD>
-__global__ void __launch_bounds__(128, 4) decim_sup_kernel(const DecimArgs a) {
-    using G = SupGeom<Q, DT, NSEGT>;
-    constexpr int D = DT, NSEG = NSEGT, P = G::P, NT = 128;
+__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
+
+template <int Q, int DT, int NSEGT, bool ROT, bool DEMOD, int NSLOTT = 2, int DBG = 0>
+__global__ void __launch_bounds__(160, NSLOTT == 3 ? 3 : 4) decim_sup_kernel(const DecimArgs a) {
+    using G = SupGeom<Q, DT, NSEGT, NSLOTT>;
+    constexpr int D = DT, NSEG = NSEGT, P = G::P;
     constexpr int LEAD = DEMOD ? 1 : 0;
-    constexpr int RY = G::RY;
-    static_assert(NSEG * P <= NT && 2 * NSEG * Q <= NT, "CTA geometry");
+    constexpr int NSLOT = G::NSLOT;
+    static_assert(NSEG * P <= 128 && NSEG <= 32, "CTA geometry");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int L = a.L;
     const int t = threadIdx.x;
+    const int warp = t >> 5, lane = t & 31;
     const int b = blockIdx.y;
     const int ch = blockIdx.z / a.nslices, slice = blockIdx.z - ch * a.nslices;
     const int plane = blockIdx.z;
@@ -571,29 +584,13 @@ __global__ void __launch_bounds__(128, 4) decim_sup_kernel(const DecimArgs a) {
     const int LOUT = L + LEAD;
     float2* X = reinterpret_cast<float2*>(smem_raw);
     float2* Pbuf = reinterpret_cast<float2*>(smem_raw + G::off_pbuf);   // [2][NSEG*Q][Ppad]
-    float2* ybuf = reinterpret_cast<float2*>(smem_raw + G::off_ybuf);   // [NSEG][RY]
-    float* abuf = reinterpret_cast<float*>(smem_raw + G::off_abuf);     // [NSEG][RY] angles of the parked outputs
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + G::off_mbar);
     float* s_misc = reinterpret_cast<float*>(smem_raw + G::off_misc);
 
-    const int seg = t / P;
-    const int pair = t - seg * P;
-    const bool in_grid = seg < NSEG;
     const int pad = (int)((bi.in_start - a.T) & 1);
-    const int ks = k0 + seg * L - LEAD;
-    const long long seg_base = bi.in_start + (long long)ks * DSg - a.T - pad + col_off;
-    const bool seg_active = in_grid && (k0 + seg * L < bi.out_count);
     const int need = (bi.out_count - k0 < L ? bi.out_count - k0 : L) + LEAD + Q - 1;
     const int nsup = (need + Q - 1) / Q < a.NSUP ? (need + Q - 1) / Q : a.NSUP;
-    int fast_lo = 0, fast_hi = 0, live_hi = 0;
-    if (seg_active) {
-        live_hi = nsup;
-        const long long lo = seg_base >= 0 ? 0 : (-seg_base + chunk_span - 1) / chunk_span;
-        const long long room = a.n_in - seg_base - chunk_tail;
-        const long long hi = room < 0 ? 0 : room / chunk_span + 1;
-        fast_lo = (int)(lo < nsup ? lo : nsup);
-        fast_hi = (int)(hi < nsup ? hi : nsup);
-    }
+    const int nactive = (bi.out_count - k0 + L - 1) / L < NSEG ? (bi.out_count - k0 + L - 1) / L : NSEG;
 
     uint64_t nco_step = 0, nco_ph0 = 0;
     if (ROT) {
@@ -601,7 +598,7 @@ __global__ void __launch_bounds__(128, 4) decim_sup_kernel(const DecimArgs a) {
         nco_ph0 = a.nco[ch].init + nco_step * (uint64_t)a.abs0;
     }
     if (t == 0) {
-        for (int s = 0; s < G::NSLOT; s++) mbar_init(&mbar[s], 1);
+        for (int s = 0; s < NSLOT; s++) mbar_init(&mbar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     bool use_override = false;
@@ -625,32 +622,32 @@ __global__ void __launch_bounds__(128, 4) decim_sup_kernel(const DecimArgs a) {
             }
         }
     }
-    __syncthreads();
+    cta_sync();
 
-    // ---- producer: warp 0, lane l issues segment l's bulk copy (Q rows) ------------------------------
-    float2* xseg = X + (size_t)seg * G::seg_pitch;
-    const int nactive = (bi.out_count - k0 + L - 1) / L < NSEG ? (bi.out_count - k0 + L - 1) / L : NSEG;
-    const long long tile_first = bi.in_start + (long long)(k0 - LEAD) * DSg - a.T - pad + col_off;
-    const long long tile_last = tile_first + (long long)(nactive - 1) * L * DSg + (long long)(nsup - 1) * chunk_span + chunk_tail;
-    const bool edge_tile = tile_first < 0 || tile_last > a.n_in;
-    const float2* p_gsrc = nullptr;
-    int p_lo = 0, p_hi = 0;
-    unsigned char* p_dst = nullptr;
-    if (t < 32 && t < nactive) {
-        const long long pbase = tile_first + (long long)t * L * DSg;
-        const long long lo = pbase >= 0 ? 0 : (-pbase + chunk_span - 1) / chunk_span;
-        const long long room = a.n_in - pbase - chunk_tail;
-        const long long hi = room < 0 ? 0 : room / chunk_span + 1;
-        p_lo = (int)(lo < nsup ? lo : nsup);
-        p_hi = (int)(hi < nsup ? hi : nsup);
-        p_gsrc = a.in + pbase;
-        p_dst = reinterpret_cast<unsigned char*>(X + (size_t)t * G::seg_pitch);
-    }
-    auto issue = [&](int it, int slot) {
-        if (t < 32) {
-            const bool fast = it >= p_lo && it < p_hi;
+    if (warp == 4) {
+        // ================= producer + finisher warp =====================================================
+        const long long tile_first = bi.in_start + (long long)(k0 - LEAD) * DSg - a.T - pad + col_off;
+        const long long tile_last = tile_first + (long long)(nactive - 1) * L * DSg + (long long)(nsup - 1) * chunk_span + chunk_tail;
+        const bool edge_tile = tile_first < 0 || tile_last > a.n_in;
+        // lane l copies segment l: stages [p_lo, p_hi) lie inside the caller's buffer (all of them on interior
+        // tiles); the rest (history before sample 0, ragged end) is filled by guarded loads
+        const bool is_prod = lane < nactive;
+        const long long pbase = tile_first + (long long)lane * L * DSg;
+        int p_lo = 0, p_hi = 0;
+        if (is_prod) {
+            const long long lo = pbase >= 0 ? 0 : (-pbase + chunk_span - 1) / chunk_span;
+            const long long room = a.n_in - pbase - chunk_tail;
+            const long long hi = room < 0 ? 0 : room / chunk_span + 1;
+            p_lo = (int)(lo < nsup ? lo : nsup);
+            p_hi = (int)(hi < nsup ? hi : nsup);
+        }
+        const float2* p_gsrc = a.in + pbase;
+        unsigned char* p_dst = reinterpret_cast<unsigned char*>(X + (size_t)lane * G::seg_pitch);
+        auto issue = [&](int it, int slot) {
+            if (it >= nsup) return;
+            const bool fast = is_prod && it >= p_lo && it < p_hi;
             const unsigned m = __ballot_sync(0xffffffffu, fast);
-            if (t == 0) mbar_arrive_expect_tx(&mbar[slot], (uint32_t)__popc(m) * G::chunk_bytes);
+            if (lane == 0) mbar_arrive_expect_tx(&mbar[slot], (uint32_t)__popc(m) * G::chunk_bytes);
             __syncwarp();
             if (fast) {
                 if (DSg == D) {
@@ -662,22 +659,90 @@ __global__ void __launch_bounds__(128, 4) decim_sup_kernel(const DecimArgs a) {
                                      (uint32_t)D * 8u, &mbar[slot]);
                 }
             }
-        }
-        if (edge_tile && in_grid) {
-            const bool fast = it >= fast_lo && it < fast_hi;
-            if (!fast && it < live_hi) {
+            if (edge_tile) {
                 VStream<float2> xs{a.hist, a.in, a.H};
-                float2* dst = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(xseg) + slot * G::stage_bytes);
-                const long long start = seg_base + (long long)it * chunk_span;
-                for (int e = pair; e < G::chunk_elems; e += P) {
-                    const int rr = e / D;
-                    const long long i = start + (long long)rr * DSg + (e - rr * D);
-                    dst[e] = (i < a.n_in) ? xs.at(i) : make_float2(0.f, 0.f);
+                for (int sg = 0; sg < nactive; sg++) {
+                    const int lo = __shfl_sync(0xffffffffu, p_lo, sg), hi = __shfl_sync(0xffffffffu, p_hi, sg);
+                    if (it >= lo && it < hi) continue;
+                    float2* dst = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(X + (size_t)sg * G::seg_pitch) + slot * G::stage_bytes);
+                    const long long start = tile_first + (long long)sg * L * DSg + (long long)it * chunk_span;
+                    for (int e = lane; e < G::chunk_elems; e += 32) {
+                        const int rr = e / D;
+                        const long long i = start + (long long)rr * DSg + (e - rr * D);
+                        dst[e] = (i < a.n_in) ? xs.at(i) : make_float2(0.f, 0.f);
+                    }
                 }
             }
+        };
+        // finisher roles: pass p covers segments [p*SA, (p+1)*SA), lane = local segment * Q + row
+        const int fls = lane / Q, fi = lane - fls * Q;
+        float lastcur[G::NPASS];
+#pragma unroll
+        for (int p = 0; p < G::NPASS; p++) lastcur[p] = 0.f;
+        auto finish = [&](int sup, int par) {
+#pragma unroll
+            for (int p = 0; p < G::NPASS; p++) {
+                const int fs = p * G::SA + fls;
+                const bool fvalid = fls < G::SA && fs < NSEG;
+                const float4* pb = reinterpret_cast<const float4*>(
+                    reinterpret_cast<const unsigned char*>(Pbuf + (fvalid ? (fs * Q + fi) : 0) * G::Ppad) + par * G::pbuf_half);
+                float2 s0 = make_float2(0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
+#pragma unroll
+                for (int m = 0; m < P / 2; m++) {
+                    const float4 v = pb[m];
+                    if (m & 1) {
+                        s2 = __fadd2_rn(s2, make_float2(v.x, v.y));
+                        s3 = __fadd2_rn(s3, make_float2(v.z, v.w));
+                    } else {
+                        s0 = __fadd2_rn(s0, make_float2(v.x, v.y));
+                        s1 = __fadd2_rn(s1, make_float2(v.z, v.w));
+                    }
+                }
+                if (P & 1) s0 = __fadd2_rn(s0, *reinterpret_cast<const float2*>(pb + P / 2));
+                const float2 y = __fadd2_rn(__fadd2_rn(s0, s1), __fadd2_rn(s2, s3));
+                const int j = sup * Q + fi - (Q - 1);                  // 0 = the segment's leading output (DEMOD)
+                const int k = k0 + fs * L - LEAD + j;                  // output index within the block
+                const bool live = fvalid && (k0 + fs * L < bi.out_count) && j >= LEAD && j < LOUT && k < bi.out_count;
+                const long long oidx = plane * a.out_stride + bi.out_start + k;
+                if (DEMOD) {
+                    const float cur = fast_arctan2_ref(y.y, y.x);
+                    float prev = __shfl_up_sync(0xffffffffu, cur, 1);
+                    // row 0 continues from the segment's last output of the previous super-iteration (row Q-1)
+                    const float carry = __shfl_sync(0xffffffffu, lastcur[p], (lane + Q - 1) & 31);
+                    if (fi == 0) prev = carry;
+                    if (use_override && fs == 0 && j == 1) prev = s_misc[0];
+                    lastcur[p] = cur;
+                    if (live) {
+                        a.audio[oidx] = fm_step_ref(cur, prev, a.phasor_speed);
+                        if (bi.out_start + k == a.part.total_out - 1) a.demod_out[ch] = cur;
+                        if (a.out_iq) a.out_iq[oidx] = y;
+                    }
+                } else {
+                    if (live) a.out_iq[oidx] = y;
+                }
+            }
+        };
+#pragma unroll 1
+        for (int s = 0; s < NSLOT; s++) issue(s, s);
+        cta_sync();
+        int slot = 0;
+#pragma unroll 1
+        for (int sup = 0; sup < nsup; sup++) {
+            cta_sync();                  // compute warps are done with slot `slot`; partials of `sup` visible
+            issue(sup + NSLOT, slot);
+            if (DBG != 2) finish(sup, sup & 1);
+            slot = slot == NSLOT - 1 ? 0 : slot + 1;
         }
-    };
+        return;
+    }
 
+    // ================= compute warps: FIR main body ======================================================
+    const int seg = t / P;
+    const int pair = t - seg * P;
+    const bool in_grid = seg < NSEG;
+    const int ks = k0 + seg * L - LEAD;
+    const long long seg_base = bi.in_start + (long long)ks * DSg - a.T - pad + col_off;
+    const bool seg_active = in_grid && (k0 + seg * L < bi.out_count);
     float2 tp[Q];
 #pragma unroll
     for (int q = 0; q < Q; q++) tp[q] = make_float2(0.f, 0.f);
@@ -698,119 +763,70 @@ __global__ void __launch_bounds__(128, 4) decim_sup_kernel(const DecimArgs a) {
 #pragma unroll
     for (int q = 0; q < Q; q++) accRe[q] = accIm[q] = make_float2(0.f, 0.f);
 
-    const unsigned char* xme = reinterpret_cast<const unsigned char*>(reinterpret_cast<const float4*>(xseg) + pair);
+    const unsigned char* xme = reinterpret_cast<const unsigned char*>(reinterpret_cast<const float4*>(X + (size_t)seg * G::seg_pitch) + pair);
     unsigned char* pme = reinterpret_cast<unsigned char*>(Pbuf + (seg * Q) * G::Ppad + pair);
     constexpr uint32_t row_bytes = (uint32_t)D * 8u;
     constexpr uint32_t prow_bytes = (uint32_t)G::Ppad * 8u;
 
-    issue(0, 0);
-    issue(1, 1);
-    __syncthreads();
-
-    // all NSEG*Q outputs of super-iteration `sup`: 2 lanes per output (packed adds); the even lane parks y and,
-    // for the FM epilogue, its angle
-    const int o2 = t >> 1, u2 = t & 1;
-    const bool v2 = o2 < NSEG * Q;
-    const int s2 = o2 / Q, i2 = o2 - s2 * Q;
-    const bool s2_live = v2 && u2 == 0 && (k0 + s2 * L < bi.out_count);
-    auto reduce_super = [&](int sup, int par) {
-        float2 sacc = make_float2(0.f, 0.f);
-        if (v2) {
-            const float2* pb = reinterpret_cast<const float2*>(reinterpret_cast<const unsigned char*>(Pbuf) + par * G::pbuf_half) + o2 * G::Ppad;
-            constexpr int NP2 = (P + 1) / 2;
-#pragma unroll
-            for (int i = 0; i < NP2; i++)
-                if (u2 + 2 * i < P) sacc = __fadd2_rn(sacc, pb[u2 + 2 * i]);
-        }
-        sacc.x += __shfl_xor_sync(0xffffffffu, sacc.x, 1);
-        sacc.y += __shfl_xor_sync(0xffffffffu, sacc.y, 1);
-        const int j = sup * Q + i2 - (Q - 1);
-        if (s2_live && j >= 0 && j < LOUT) {
-            const int slot = s2 * RY + (j % RY);
-            ybuf[slot] = sacc;
-            if (DEMOD) abuf[slot] = fast_arctan2_ref(sacc.y, sacc.x);
-        }
-    };
-    // epilogue of a finished super-iteration: one thread per output, taken from the top of the CTA (the low warps
-    // carry the producer and most of the reduce)
-    const int et = NT - 1 - t;
-    const int es = et / Q, er = et - es * Q;
-    auto epilogue = [&](int sup) {
-        if (et >= NSEG * Q) return;
-        const int j = sup * Q + er - (Q - 1);
-        const int k = k0 + es * L - LEAD + j;
-        if (j < LEAD || j >= LOUT || k >= bi.out_count) return;
-        const long long oidx = plane * a.out_stride + bi.out_start + k;
-        if (DEMOD) {
-            const float cur = abuf[es * RY + (j % RY)];
-            const float prev = (use_override && es == 0 && j == 1) ? s_misc[0] : abuf[es * RY + ((j - 1) % RY)];
-            a.audio[oidx] = fm_step_ref(cur, prev, a.phasor_speed);
-            if (bi.out_start + k == a.part.total_out - 1) a.demod_out[ch] = cur;
-            if (a.out_iq) a.out_iq[oidx] = ybuf[es * RY + (j % RY)];
-        } else {
-            a.out_iq[oidx] = ybuf[es * RY + (j % RY)];
-        }
-    };
-
+    cta_sync();                          // pairs with the producer's prologue barrier
+    int slot = 0;
+    uint32_t parity = 0;
 #pragma unroll 1
-    for (int sup2 = 0; sup2 < nsup; sup2 += 2) {
-        if (ROT && (sup2 & 7) == 0 && seg_active) {
-            const long long i0 = col0 + (long long)sup2 * Q * DSg;
+    for (int sup = 0; sup < nsup; sup++) {
+        if (ROT && (sup & 7) == 0 && seg_active) {
+            // exact phasor re-seed (closed form) every 8*Q rows bounds the recurrence's rounding walk
+            const long long i0 = col0 + (long long)sup * Q * DSg;
             const float2 p0 = phasor_from_turns(nco_ph0 + nco_step * (uint64_t)i0);
             const float2 p1 = phasor_from_turns(nco_ph0 + nco_step * (uint64_t)(i0 + 1));
             PR = make_float2(p0.x, p1.x);
             PI = make_float2(p0.y, p1.y);
         }
-        const uint32_t parity = (uint32_t)((sup2 >> 1) & 1);
+        mbar_wait(&mbar[slot], parity);
+        if (seg_active && DBG != 1) {
+            const unsigned char* xs_ = xme + slot * G::stage_bytes;
+            unsigned char* ps_ = pme + (sup & 1) * G::pbuf_half;
 #pragma unroll
-        for (int slot = 0; slot < 2; slot++) {
-            const int sup = sup2 + slot;
-            if (sup < nsup) {
-                mbar_wait(&mbar[slot], parity);
-                if (seg_active) {
-                    const unsigned char* xs_ = xme + slot * G::stage_bytes;
-                    unsigned char* ps_ = pme + slot * G::pbuf_half;
+            for (int i = 0; i < Q; i++) {
+                const float4 v = *reinterpret_cast<const float4*>(xs_ + i * row_bytes);
+                float2 RE, IM;
+                if (ROT) {
+                    // x' = x * p for both columns; results land directly in the packed (col r, col r+1) pairs
+                    RE.x = fmaf(v.x, PR.x, -(v.y * PI.x));
+                    IM.x = fmaf(v.x, PI.x, v.y * PR.x);
+                    RE.y = fmaf(v.z, PR.y, -(v.w * PI.y));
+                    IM.y = fmaf(v.z, PI.y, v.w * PR.y);
+                    // p *= w for both columns in 4 packed ops
+                    const float2 nPR = __ffma2_rn(PI, neg2(wi2), __fmul2_rn(PR, wr2));
+                    PI = __ffma2_rn(PI, wr2, __fmul2_rn(PR, wi2));
+                    PR = nPR;
+                } else {
+                    RE = make_float2(v.x, v.z);
+                    IM = make_float2(v.y, v.w);
+                }
 #pragma unroll
-                    for (int i = 0; i < Q; i++) {
-                        const float4 v = *reinterpret_cast<const float4*>(xs_ + i * row_bytes);
-                        float2 RE, IM;
-                        if (ROT) {
-                            RE.x = fmaf(v.x, PR.x, -(v.y * PI.x));
-                            IM.x = fmaf(v.x, PI.x, v.y * PR.x);
-                            RE.y = fmaf(v.z, PR.y, -(v.w * PI.y));
-                            IM.y = fmaf(v.z, PI.y, v.w * PR.y);
-                            const float2 nPR = __ffma2_rn(PI, neg2(wi2), __fmul2_rn(PR, wr2));
-                            PI = __ffma2_rn(PI, wr2, __fmul2_rn(PR, wi2));
-                            PR = nPR;
-                        } else {
-                            RE = make_float2(v.x, v.z);
-                            IM = make_float2(v.y, v.w);
-                        }
-#pragma unroll
-                        for (int q = 0; q < Q; q++) {
-                            const int sl = (i - q + Q) % Q;
-                            if (q == 0) {
-                                accRe[sl] = __fmul2_rn(RE, tp[0]);
-                                accIm[sl] = __fmul2_rn(IM, tp[0]);
-                            } else {
-                                accRe[sl] = __ffma2_rn(RE, tp[q], accRe[sl]);
-                                accIm[sl] = __ffma2_rn(IM, tp[q], accIm[sl]);
-                            }
-                        }
-                        const int e = (i + 1) % Q;
-                        *reinterpret_cast<float2*>(ps_ + i * prow_bytes) =
-                            make_float2(accRe[e].x + accRe[e].y, accIm[e].x + accIm[e].y);
+                for (int q = 0; q < Q; q++) {
+                    const int sl = (i - q + Q) % Q;
+                    if (q == 0) {
+                        accRe[sl] = __fmul2_rn(RE, tp[0]);
+                        accIm[sl] = __fmul2_rn(IM, tp[0]);
+                    } else {
+                        accRe[sl] = __ffma2_rn(RE, tp[q], accRe[sl]);
+                        accIm[sl] = __ffma2_rn(IM, tp[q], accIm[sl]);
                     }
                 }
-                __syncthreads();              // slot consumed, this super-iteration's partials visible
-                issue(sup + 2, slot);         // refill the slot just drained
-                reduce_super(sup, slot);
-                if (sup > 0) epilogue(sup - 1);
+                const int e = (i + 1) % Q;    // the output whose last tap (q = Q-1) was just applied
+                *reinterpret_cast<float2*>(ps_ + i * prow_bytes) =
+                    make_float2(accRe[e].x + accRe[e].y, accIm[e].x + accIm[e].y);
             }
         }
+        cta_sync();                      // slot consumed, this super-iteration's partials visible
+        if (slot == NSLOT - 1) {
+            slot = 0;
+            parity ^= 1u;
+        } else {
+            slot++;
+        }
     }
-    __syncthreads();
-    epilogue(nsup - 1);
 }
 
 // ---- host side -------------------------------------------------------------------------------------
@@ -933,12 +949,12 @@ static int launch_decim_t(const DecimArgs& a, dim3 grid, int NT, size_t smem, cu
     return 0;
 }
 
-template <int Q, int DT, int NSEGT, bool ROT, bool DEMOD>
+template <int Q, int DT, int NSEGT, bool ROT, bool DEMOD, int NSLOTT = 2, int DBG = 0>
 static int launch_decim_sup_t(const DecimArgs& a, dim3 grid, cudaStream_t s) {
-    auto kern = decim_sup_kernel<Q, DT, NSEGT, ROT, DEMOD>;
-    constexpr size_t smem = SupGeom<Q, DT, NSEGT>::smem_bytes;
+    auto kern = decim_sup_kernel<Q, DT, NSEGT, ROT, DEMOD, NSLOTT, DBG>;
+    constexpr size_t smem = SupGeom<Q, DT, NSEGT, NSLOTT>::smem_bytes;
     QDSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, 128, smem, s>>>(a);
+    kern<<<grid, 160, smem, s>>>(a);
     QDSP_LAUNCH_OK();
     return 0;
 }
@@ -1037,6 +1053,13 @@ int launch_decim(DecimPlan* plan, const float2* hist, int H, const float2* in, c
     static const bool supred_env = getenv("QDSP_DECIM_SUPRED") ? atoi(getenv("QDSP_DECIM_SUPRED")) != 0 : true;
     const bool supred = supred_env && plan->P <= 64 && plan->NT >= 2 * plan->NSEG * plan->Q;
     const size_t smem = supred ? smem_sup : smem_stage;
+#ifdef QDSP_DECIM_DEBUG_VARIANTS   // profiling aids: 1 = no FIR math (data movement only), 2 = no finishing pass
+    if (const char* e = getenv("QDSP_DECIM_DBG")) {
+        if (atoi(e) == 1 && fused) return launch_decim_sup_t<9, 50, 5, true, true, 2, 1>(a, grid, s);
+        if (atoi(e) == 2 && fused) return launch_decim_sup_t<9, 50, 5, true, true, 2, 2>(a, grid, s);
+        if (atoi(e) == 3 && fused) return launch_decim_sup_t<9, 50, 5, true, true, 3, 0>(a, grid, s);
+    }
+#endif
     if (plan->Q == 9 && plan->D == 50 && plan->NSEG == 5 && supred && plan->NT == 128 && decim_v2_enabled())
         return fused ? launch_decim_sup_t<9, 50, 5, true, true>(a, grid, s) : launch_decim_sup_t<9, 50, 5, false, false>(a, grid, s);
     if (plan->Q == 9 && plan->D == 50 && plan->NSEG == 5)
