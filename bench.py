@@ -282,10 +282,10 @@ def ours(args):
     k_ms = float(np.mean(kernel_ms))
     achieved = ALG_BYTES_PER_SAMPLE * n / (k_ms * 1e-3) / 1e9
     # DRAM bytes per launch of the fused kernel at the default workload, from the committed ncu --set full capture
-    # (profiles/r01_fused_vfofm_ncu_full.txt: dram__bytes_read.sum 2.227413 GB + dram__bytes_write.sum 27.38 MB)
-    traffic = 2.227413e9 + 27.383552e6 if n == N_SAMPLES else None
+    # (profiles/r01_fused_vfofm_v2_ncu_full.txt: dram__bytes_read.sum 2.227204 GB + dram__bytes_write.sum 26.41 MB)
+    traffic = 2.227204e9 + 26.410752e6 if n == N_SAMPLES else None
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": traffic, "peak_source": peak_src, "kernel": "qdsp::decim_kernel<9,50,5,ROT,DEMOD,SUPRED,128,5> (fused xlate+resample+demod)",
+            "traffic": traffic, "peak_source": peak_src, "kernel": "qdsp::decim_sup_kernel<9,50,5,ROT,DEMOD> (fused xlate+resample+demod)",
             "kernel_ms": k_ms, "alg_bytes_per_launch": ALG_BYTES_PER_SAMPLE * n,
             "fp32_tflops": ALG_FLOP_PER_SAMPLE * n / (k_ms * 1e-3) / 1e12}
     cpu = None
