@@ -231,6 +231,67 @@ int qdsp_costas_set_state(qdsp_costas* h, const float state[4]);
 int qdsp_costas_set_chunking(qdsp_costas* h, int chunk, int warmup);
 float qdsp_costas_last_residual(qdsp_costas* h);
 
+/* ---- element-wise, layout and per-block-statistic blocks ("next" rows of the scope table) ------------------- *
+ * Each call replaces one run() body; two-input blocks require equal counts (the reference drops mismatched      *
+ * blocks, math.h:26-30).                                                                                        */
+enum { QDSP_MATH_ADD = 0, QDSP_MATH_SUB = 1, QDSP_MATH_MUL = 2 };
+/* Add<T> / Substract<T> / Multiply<T>::run, src/dsp/math.h:21-43 / 68-90 / 115-137 (dtype QDSP_CF32 = complex_t or
+ * stereo_t; Multiply on QDSP_CF32 is the complex product of volk_32fc_x2_multiply_32fc) */
+long long qdsp_math_process(int op, int dtype, const void* a_dev, const void* b_dev, void* out_dev, long long count,
+                            qdsp_stream_t s);
+enum {
+    QDSP_LAYOUT_MONO_TO_STEREO = 0,     /* MonoToStereo::run, audio.h:26-35: float -> stereo_t {x, x}                 */
+    QDSP_LAYOUT_CHANNELS_TO_STEREO = 1, /* ChannelsToStereo::run, audio.h:70-86: in0 = left, in1 = right            */
+    QDSP_LAYOUT_STEREO_TO_MONO = 2,     /* StereoToMono::run, audio.h:125-137: (l + r) * 0.5f                        */
+    QDSP_LAYOUT_STEREO_TO_CHANNELS = 3, /* StereoToChannels::run, audio.h:169-179: out0 = left, out1 = right        */
+    QDSP_LAYOUT_COMPLEX_TO_STEREO = 4,  /* ComplexToStereo::run, convertion.h:28-37 (a copy)                         */
+    QDSP_LAYOUT_COMPLEX_TO_REAL = 5,    /* ComplexToReal::run, convertion.h:67-76                                    */
+    QDSP_LAYOUT_COMPLEX_TO_IMAG = 6,    /* ComplexToImag::run, convertion.h:106-115                                  */
+    QDSP_LAYOUT_REAL_TO_COMPLEX = 7     /* RealToComplex::run, convertion.h:153-162: {x, 0}                          */
+};
+long long qdsp_layout_process(int op, const void* in0_dev, const void* in1_dev, void* out0_dev, void* out1_dev,
+                              long long count, qdsp_stream_t s);
+/* Volume<float|stereo_t>::run, src/dsp/processing.h:388-411; level = qdsp_volume_level(volume) = powf(volume, 2)
+ * (setVolume, :371-374 -- note that the reference's init() leaves level at 1.0 until setVolume is called) */
+float qdsp_volume_level(float volume);
+long long qdsp_volume_process(int dtype, float level, int muted, const void* in_dev, void* out_dev, long long count,
+                              qdsp_stream_t s);
+/* Threshold::run, src/dsp/processing.h:589-599: out[i] = in[i] > 0 (uint8) */
+long long qdsp_threshold_process(const float* in_dev, unsigned char* out_dev, long long count, qdsp_stream_t s);
+/* DelayImag::run, src/dsp/processing.h:321-337: out[i] = {in[i].re, in[i-1].im}; state lastIm */
+typedef struct qdsp_delayimag qdsp_delayimag;
+qdsp_delayimag* qdsp_delayimag_create(void);
+void qdsp_delayimag_destroy(qdsp_delayimag* h);
+long long qdsp_delayimag_process(qdsp_delayimag* h, const void* in_dev, void* out_dev, long long count, qdsp_stream_t s);
+int qdsp_delayimag_get_state(qdsp_delayimag* h, float* lastIm);
+int qdsp_delayimag_set_state(qdsp_delayimag* h, float lastIm);
+/* AMDemod::run, src/dsp/demodulator.h:355-374: magnitude minus the mean magnitude of the run() block (so the
+ * partition matters); the mean is summed in double here, sequentially in float by the reference */
+typedef struct qdsp_amdemod qdsp_amdemod;
+qdsp_amdemod* qdsp_amdemod_create(void);
+void qdsp_amdemod_destroy(qdsp_amdemod* h);
+long long qdsp_amdemod_process(qdsp_amdemod* h, const void* in_dev, float* out_dev, long long count, const int* blocks,
+                               int nblocks, int block_size, qdsp_stream_t s);
+/* Squelch::run, src/dsp/processing.h:460-479: a run() block passes iff 10*log10f(mean |x|) >= level, else zeros */
+typedef struct qdsp_squelch qdsp_squelch;
+qdsp_squelch* qdsp_squelch_create(float level);
+void qdsp_squelch_destroy(qdsp_squelch* h);
+void qdsp_squelch_set_level(qdsp_squelch* h, float level);
+float qdsp_squelch_get_level(qdsp_squelch* h);
+long long qdsp_squelch_process(qdsp_squelch* h, const void* in_dev, void* out_dev, long long count, const int* blocks,
+                               int nblocks, int block_size, qdsp_stream_t s);
+/* SSBDemod::run, src/dsp/demodulator.h:475-487: VOLK rotator by +-pi*bandWidth/sampleRate per sample (USB / LSB; DSB
+ * does not rotate), then the real part; the NCO is the closed form used by the translator */
+enum { QDSP_SSB_USB = 0, QDSP_SSB_LSB = 1, QDSP_SSB_DSB = 2 };   /* SSBDemod::MODE_*, demodulator.h:391-395 */
+typedef struct qdsp_ssbdemod qdsp_ssbdemod;
+qdsp_ssbdemod* qdsp_ssbdemod_create(float sampleRate, float bandWidth, int mode);
+void qdsp_ssbdemod_destroy(qdsp_ssbdemod* h);
+int qdsp_ssbdemod_configure(qdsp_ssbdemod* h, float sampleRate, float bandWidth, int mode);   /* setSampleRate / setBandWidth / setMode */
+void qdsp_ssbdemod_get_phase_delta(qdsp_ssbdemod* h, float* re, float* im);
+void qdsp_ssbdemod_get_phase(qdsp_ssbdemod* h, float* re, float* im);
+void qdsp_ssbdemod_set_phase(qdsp_ssbdemod* h, float re, float im);
+long long qdsp_ssbdemod_process(qdsp_ssbdemod* h, const void* in_dev, float* out_dev, long long count, qdsp_stream_t s);
+
 /* ---- device-side synthetic IQ (bench inputs; same integer recipe as qdsp_b200/synth.py) ------ */
 int qdsp_synth_uniform_cf32(void* out_dev, unsigned long long seed, long long start, long long count, qdsp_stream_t s);
 int qdsp_synth_fm_cf32(void* out_dev, long long start, long long count, long long fs, long long fc, long long fm,

@@ -329,6 +329,102 @@ class Ref:
         return (y, sec.value) if timing else y
 
 
+    # -- element-wise / layout / per-block-statistic blocks ("next" rows) ----------------------------------
+    def _decl_pointwise(self):
+        L = self.lib
+        if getattr(self, "_pw", False):
+            return
+        ucp = C.POINTER(C.c_ubyte)
+        L.ref_math.argtypes = [_i, _i, _fp, _fp, _ip, _i, _fp]
+        L.ref_math.restype = _ll
+        L.ref_layout.argtypes = [_i, _fp, _fp, _ip, _i, _fp, _fp]
+        L.ref_layout.restype = _ll
+        L.ref_volume.argtypes = [_i, _f, _i, _i, _fp, _ip, _i, _fp]
+        L.ref_volume.restype = _ll
+        L.ref_threshold.argtypes = [_fp, _ip, _i, ucp]
+        L.ref_threshold.restype = _ll
+        for name in ("ref_delay_imag", "ref_amdemod"):
+            getattr(L, name).argtypes = [_fp, _ip, _i, _fp]
+            getattr(L, name).restype = _ll
+        L.ref_squelch.argtypes = [_f, _fp, _ip, _i, _fp]
+        L.ref_squelch.restype = _ll
+        L.ref_ssbdemod.argtypes = [_f, _f, _i, _fp, _ip, _i, _fp]
+        L.ref_ssbdemod.restype = _ll
+        self._pw = True
+
+    @staticmethod
+    def _f32view(x):
+        x = np.ascontiguousarray(x)
+        return x, _fptr(x.view(np.float32))
+
+    def math(self, op, a, b, block):
+        self._decl_pointwise()
+        a, pa = self._f32view(a)
+        b, pb = self._f32view(b)
+        bl = as_blocks(len(a), block)
+        y = np.empty(len(a), a.dtype)
+        n = self.lib.ref_math(op, int(np.iscomplexobj(a)), pa, pb, _iptr(bl), len(bl), _fptr(y.view(np.float32)))
+        assert n == len(a)
+        return y
+
+    def layout(self, op, x0, x1, block):
+        """Returns out0 (and out1 for op 3). Element types follow the QDSP_LAYOUT_* op."""
+        self._decl_pointwise()
+        x0, p0 = self._f32view(x0)
+        p1 = None
+        if x1 is not None:
+            x1, p1 = self._f32view(x1)
+        n = len(x0)
+        bl = as_blocks(n, block)
+        out_complex = op in (0, 1, 4, 7)
+        y0 = np.empty(n, np.complex64 if out_complex else np.float32)
+        y1 = np.empty(n, np.float32)
+        m = self.lib.ref_layout(op, p0, p1, _iptr(bl), len(bl), _fptr(y0.view(np.float32)), _fptr(y1))
+        assert m == n
+        return (y0, y1) if op == 3 else y0
+
+    def volume(self, x, volume, call_set, muted, block):
+        self._decl_pointwise()
+        x, px = self._f32view(x)
+        bl = as_blocks(len(x), block)
+        y = np.empty(len(x), x.dtype)
+        n = self.lib.ref_volume(int(np.iscomplexobj(x)), volume, int(call_set), int(muted), px, _iptr(bl), len(bl),
+                                _fptr(y.view(np.float32)))
+        assert n == len(x)
+        return y
+
+    def threshold(self, x, block):
+        self._decl_pointwise()
+        x, px = self._f32view(np.asarray(x, np.float32))
+        bl = as_blocks(len(x), block)
+        y = np.empty(len(x), np.uint8)
+        n = self.lib.ref_threshold(px, _iptr(bl), len(bl), y.ctypes.data_as(C.POINTER(C.c_ubyte)))
+        assert n == len(x)
+        return y
+
+    def _c2x(self, fn, x, block, out_dtype, *pre):
+        self._decl_pointwise()
+        x, px = self._cin(x)
+        bl = as_blocks(len(x), block)
+        y = np.empty(len(x), out_dtype)
+        n = fn(*pre, px, _iptr(bl), len(bl), _fptr(y.view(np.float32)))
+        assert n == len(x)
+        return y
+
+    def delay_imag(self, x, block):
+        return self._c2x(self.lib.ref_delay_imag, x, block, np.complex64)
+
+    def amdemod(self, x, block):
+        return self._c2x(self.lib.ref_amdemod, x, block, np.float32)
+
+    def squelch(self, level, x, block):
+        return self._c2x(self.lib.ref_squelch, x, block, np.complex64, _f(level))
+
+    def ssbdemod(self, fs, bw, mode, x, block):
+        return self._c2x(self.lib.ref_ssbdemod, x, block, np.float32, _f(fs), _f(bw), int(mode))
+
+
+
 @lru_cache(maxsize=None)
 def ref(variant: str = "generic") -> Ref:
     return Ref(variant)
@@ -579,6 +675,103 @@ class Port:
         self.lib.port_costas(order, bw, px, len(x), _fptr(y.view(np.float32)), _fptr(st))
         return y, st
 
+
+    # -- element-wise / layout / per-block-statistic blocks ("next" rows) ----------------------------------
+    def _decl_pointwise(self):
+        L = self.lib
+        if getattr(self, "_pw", False):
+            return
+        ucp = C.POINTER(C.c_ubyte)
+        L.port_math.argtypes = [_i, _i, _fp, _fp, _fp, _ll]
+        L.port_layout.argtypes = [_i, _fp, _fp, _fp, _fp, _ll]
+        L.port_volume_level.argtypes = [_f]
+        L.port_volume_level.restype = _f
+        L.port_volume.argtypes = [_f, _i, _fp, _fp, _ll]
+        L.port_threshold.argtypes = [_fp, ucp, _ll]
+        L.port_delay_imag.argtypes = [_fp, _fp, _ll, _fp]
+        L.port_amdemod.argtypes = [_fp, _ip, _i, _fp]
+        L.port_squelch.argtypes = [_f, _fp, _ip, _i, _fp]
+        L.port_ssb_phase_delta.argtypes = [_f, _f, _i, _fp, _fp]
+        L.port_ssbdemod.argtypes = [_f, _f, _i, _fp, _ip, _i, _fp]
+        self._pw = True
+
+    @staticmethod
+    def _f32view(x):
+        x = np.ascontiguousarray(x)
+        return x, _fptr(x.view(np.float32))
+
+    def math(self, op, a, b):
+        self._decl_pointwise()
+        a, pa = self._f32view(a)
+        b, pb = self._f32view(b)
+        y = np.empty(len(a), a.dtype)
+        self.lib.port_math(op, int(np.iscomplexobj(a)), pa, pb, _fptr(y.view(np.float32)), len(a))
+        return y
+
+    def layout(self, op, x0, x1=None):
+        self._decl_pointwise()
+        x0, p0 = self._f32view(x0)
+        p1 = None
+        if x1 is not None:
+            x1, p1 = self._f32view(x1)
+        n = len(x0)
+        y0 = np.empty(n, np.complex64 if op in (0, 1, 4, 7) else np.float32)
+        y1 = np.empty(n, np.float32)
+        self.lib.port_layout(op, p0, p1, _fptr(y0.view(np.float32)), _fptr(y1), n)
+        return (y0, y1) if op == 3 else y0
+
+    def volume(self, x, volume, call_set, muted):
+        self._decl_pointwise()
+        x, px = self._f32view(x)
+        level = float(self.lib.port_volume_level(volume)) if call_set else 1.0
+        y = np.empty(len(x), x.dtype)
+        self.lib.port_volume(level, int(muted), px, _fptr(y.view(np.float32)), x.view(np.float32).size)
+        return y
+
+    def threshold(self, x):
+        self._decl_pointwise()
+        x, px = self._f32view(np.asarray(x, np.float32))
+        y = np.empty(len(x), np.uint8)
+        self.lib.port_threshold(px, y.ctypes.data_as(C.POINTER(C.c_ubyte)), len(x))
+        return y
+
+    def delay_imag(self, x, last_im=0.0):
+        self._decl_pointwise()
+        x, px = self._cin(x)
+        y = np.empty(len(x), np.complex64)
+        st = _f(last_im)
+        self.lib.port_delay_imag(px, _fptr(y.view(np.float32)), len(x), C.byref(st))
+        return y
+
+    def amdemod(self, x, block):
+        self._decl_pointwise()
+        x, px = self._cin(x)
+        bl = as_blocks(len(x), block)
+        y = np.empty(len(x), np.float32)
+        self.lib.port_amdemod(px, _iptr(bl), len(bl), _fptr(y))
+        return y
+
+    def squelch(self, level, x, block):
+        self._decl_pointwise()
+        x, px = self._cin(x)
+        bl = as_blocks(len(x), block)
+        y = np.empty(len(x), np.complex64)
+        self.lib.port_squelch(level, px, _iptr(bl), len(bl), _fptr(y.view(np.float32)))
+        return y
+
+    def ssb_phase_delta(self, fs, bw, mode) -> complex:
+        self._decl_pointwise()
+        re, im = _f(), _f()
+        self.lib.port_ssb_phase_delta(fs, bw, mode, C.byref(re), C.byref(im))
+        return complex(re.value, im.value)
+
+    def ssbdemod(self, fs, bw, mode, x, block):
+        self._decl_pointwise()
+        x, px = self._cin(x)
+        bl = as_blocks(len(x), block)
+        y = np.empty(len(x), np.float32)
+        self.lib.port_ssbdemod(fs, bw, mode, px, _iptr(bl), len(bl), _fptr(y))
+        return y
 
 @lru_cache(maxsize=None)
 def port() -> Port:

@@ -560,3 +560,127 @@ void port_costas(int order, float bw, const cf32* x, long long n, cf32* y, float
     state[2] = vr;
     state[3] = vi;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Element-wise / layout / per-block-statistic blocks ("next" rows of the scope table)
+ * ---------------------------------------------------------------------------------------- */
+
+/* Add / Substract / Multiply<T>::run, src/dsp/math.h:32-37, 79-84, 126-131 over one matched pair of
+ * blocks. op 0/1/2; dtype 0 = float, 1 = complex_t (add/subtract of complex or stereo streams are
+ * float add/subtract over 2n floats; Multiply<complex_t> is volk_32fc_x2_multiply_32fc) */
+void port_math(int op, int dtype, const float* a, const float* b, float* out, long long n) {
+    if (dtype == 1 && op == 2) {
+        for (long long k = 0; k < n; k++) {
+            const float ar = a[2 * k], ai = a[2 * k + 1], br = b[2 * k], bi = b[2 * k + 1];
+            out[2 * k] = ar * br - ai * bi;
+            out[2 * k + 1] = ar * bi + ai * br;
+        }
+        return;
+    }
+    const long long nf = dtype == 1 ? 2 * n : n;
+    for (long long k = 0; k < nf; k++) out[k] = op == 0 ? a[k] + b[k] : (op == 1 ? a[k] - b[k] : a[k] * b[k]);
+}
+
+/* audio.h / convertion.h run() bodies; op numbering = QDSP_LAYOUT_* (include/qdsp_b200.h):
+ * 0 MonoToStereo audio.h:30, 1 ChannelsToStereo audio.h:80, 2 StereoToMono audio.h:129-131,
+ * 3 StereoToChannels audio.h:173, 4 ComplexToStereo convertion.h:32, 5 ComplexToReal convertion.h:71,
+ * 6 ComplexToImag convertion.h:110, 7 RealToComplex convertion.h:157 (nullBuffer is zeros, :137-140) */
+void port_layout(int op, const float* in0, const float* in1, float* out0, float* out1, long long n) {
+    for (long long k = 0; k < n; k++) {
+        switch (op) {
+            case 0: out0[2 * k] = in0[k]; out0[2 * k + 1] = in0[k]; break;
+            case 1: out0[2 * k] = in0[k]; out0[2 * k + 1] = in1[k]; break;
+            case 2: out0[k] = (in0[2 * k] + in0[2 * k + 1]) * 0.5f; break;
+            case 3: out0[k] = in0[2 * k]; out1[k] = in0[2 * k + 1]; break;
+            case 4: out0[2 * k] = in0[2 * k]; out0[2 * k + 1] = in0[2 * k + 1]; break;
+            case 5: out0[k] = in0[2 * k]; break;
+            case 6: out0[k] = in0[2 * k + 1]; break;
+            case 7: out0[2 * k] = in0[k]; out0[2 * k + 1] = 0.0f; break;
+        }
+    }
+}
+
+/* Volume<T>: level = powf(volume, 2) only once setVolume() ran (processing.h:371-374; init :355-359 leaves
+ * level = 1.0f); run :388-411 over nf floats */
+float port_volume_level(float volume) { return powf(volume, 2); }
+void port_volume(float level, int muted, const float* in, float* out, long long nf) {
+    if (muted) {
+        memset(out, 0, sizeof(float) * (size_t)nf);
+        return;
+    }
+    for (long long k = 0; k < nf; k++) out[k] = in[k] * level;
+}
+
+/* Threshold::run, processing.h:593-595 */
+void port_threshold(const float* in, unsigned char* out, long long n) {
+    for (long long k = 0; k < n; k++) out[k] = (in[k] > 0.0f);
+}
+
+/* DelayImag::run, processing.h:325-330; *lastIm carried across calls */
+void port_delay_imag(const cf32* in, cf32* out, long long n, float* lastIm) {
+    for (long long k = 0; k < n; k++) {
+        const cf32 v = in[k];
+        out[k].re = v.re;
+        out[k].im = *lastIm;
+        *lastIm = v.im;
+    }
+}
+
+static float port_mean_mag(const cf32* x, int n, float* mag) {
+    /* volk_32fc_magnitude_32f + volk_32f_accumulator_s32f (generic: sequential float sum), then / (float)count */
+    float acc = 0.0f;
+    for (int k = 0; k < n; k++) {
+        const float m = sqrtf(x[k].re * x[k].re + x[k].im * x[k].im);
+        if (mag) mag[k] = m;
+        acc += m;
+    }
+    return acc / (float)n;
+}
+
+/* AMDemod::run, demodulator.h:355-374, per run() block */
+void port_amdemod(const cf32* x, const int* blocks, int nblocks, float* out) {
+    long long off = 0;
+    for (int b = 0; b < nblocks; b++) {
+        const float avg = port_mean_mag(x + off, blocks[b], out + off);
+        for (int k = 0; k < blocks[b]; k++) out[off + k] -= avg;
+        off += blocks[b];
+    }
+}
+
+/* Squelch::run, processing.h:460-479, per run() block */
+void port_squelch(float level, const cf32* x, const int* blocks, int nblocks, cf32* out) {
+    long long off = 0;
+    for (int b = 0; b < nblocks; b++) {
+        const float sum = port_mean_mag(x + off, blocks[b], NULL);
+        if (10.0f * log10f(sum) >= level) memcpy(out + off, x + off, sizeof(cf32) * (size_t)blocks[b]);
+        else memset(out + off, 0, sizeof(cf32) * (size_t)blocks[b]);
+        off += blocks[b];
+    }
+}
+
+/* SSBDemod: phaseDelta per mode (demodulator.h:402-412, float cos/sin overloads), run :479-480 = VOLK rotator per
+ * run() block (phase carried) + real part */
+void port_ssb_phase_delta(float sampleRate, float bandWidth, int mode, float* re, float* im) {
+    if (mode == 0) {
+        *re = cosf((bandWidth / sampleRate) * FL_M_PI);
+        *im = sinf((bandWidth / sampleRate) * FL_M_PI);
+    } else if (mode == 1) {
+        *re = cosf(-(bandWidth / sampleRate) * FL_M_PI);
+        *im = sinf(-(bandWidth / sampleRate) * FL_M_PI);
+    } else {
+        *re = 1.0f;
+        *im = 0.0f;
+    }
+}
+void port_ssbdemod(float sampleRate, float bandWidth, int mode, const cf32* x, const int* blocks, int nblocks, float* out) {
+    float ir, ii, pr = 1.0f, pi = 0.0f;
+    port_ssb_phase_delta(sampleRate, bandWidth, mode, &ir, &ii);
+    long long off = 0;
+    for (int b = 0; b < nblocks; b++) {
+        cf32* tmp = (cf32*)malloc(sizeof(cf32) * (size_t)(blocks[b] > 0 ? blocks[b] : 1));
+        port_rotator(x + off, tmp, ir, ii, &pr, &pi, blocks[b]);
+        for (int k = 0; k < blocks[b]; k++) out[off + k] = tmp[k].re;
+        free(tmp);
+        off += blocks[b];
+    }
+}

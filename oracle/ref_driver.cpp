@@ -20,6 +20,9 @@
 #include <dsp/pll.h>
 #include <dsp/vfo.h>
 #include <dsp/routing.h>
+#include <dsp/math.h>
+#include <dsp/audio.h>
+#include <dsp/convertion.h>
 
 #include <chrono>
 #include <thread>
@@ -392,6 +395,134 @@ long long ref_costas(int order, float loopBandwidth, const float* in, const int*
         case 8: return costas_impl<8>(loopBandwidth, in, blocks, nblocks, out, seconds);
     }
     return -1;
+}
+
+}  // extern "C"
+
+// ---- element-wise / layout / per-block-statistic blocks ("next" rows) --------------------------------------------
+namespace {
+template <class Tin, class Tout, class B>
+long long run1(stream<Tin>* src, B& blk, stream<Tout>* out_s, const void* in, const int* blocks, int nblocks, void* out) {
+    blk.start();
+    long long n = pump(src, out_s, (const Tin*)in, blocks, nblocks, (Tout*)out, nullptr, nullptr);
+    blk.stop();
+    return n;
+}
+template <class T, class B>
+long long run2(stream<T>* sa, stream<T>* sb, B& blk, const void* a, const void* b, const int* blocks, int nblocks, void* out) {
+    blk.start();
+    std::thread fa([&] { feed(sa, (const T*)a, blocks, nblocks); });
+    std::thread fb([&] { feed(sb, (const T*)b, blocks, nblocks); });
+    long long n = drain(&blk.out, (T*)out, nblocks, nullptr);
+    fa.join();
+    fb.join();
+    blk.stop();
+    return n;
+}
+}  // namespace
+
+extern "C" {
+
+// math.h: Add / Substract / Multiply. op 0/1/2; dtype 0 = float, 1 = complex_t
+long long ref_math(int op, int dtype, const float* a, const float* b, const int* blocks, int nblocks, float* out) {
+    if (dtype == 1) {
+        stream<complex_t> sa, sb;
+        if (op == 0) { Add<complex_t> k(&sa, &sb); return run2(&sa, &sb, k, a, b, blocks, nblocks, out); }
+        if (op == 1) { Substract<complex_t> k(&sa, &sb); return run2(&sa, &sb, k, a, b, blocks, nblocks, out); }
+        Multiply<complex_t> k(&sa, &sb);
+        return run2(&sa, &sb, k, a, b, blocks, nblocks, out);
+    }
+    stream<float> sa, sb;
+    if (op == 0) { Add<float> k(&sa, &sb); return run2(&sa, &sb, k, a, b, blocks, nblocks, out); }
+    if (op == 1) { Substract<float> k(&sa, &sb); return run2(&sa, &sb, k, a, b, blocks, nblocks, out); }
+    Multiply<float> k(&sa, &sb);
+    return run2(&sa, &sb, k, a, b, blocks, nblocks, out);
+}
+// audio.h / convertion.h; op numbering = QDSP_LAYOUT_* of include/qdsp_b200.h
+long long ref_layout(int op, const float* in0, const float* in1, const int* blocks, int nblocks, float* out0, float* out1) {
+    switch (op) {
+        case 0: { stream<float> s; MonoToStereo k(&s); return run1(&s, k, &k.out, in0, blocks, nblocks, out0); }
+        case 1: {
+            stream<float> sl, sr;
+            ChannelsToStereo k(&sl, &sr);
+            k.start();
+            std::thread fa([&] { feed(&sl, in0, blocks, nblocks); });
+            std::thread fb([&] { feed(&sr, in1, blocks, nblocks); });
+            long long n = drain(&k.out, (stereo_t*)out0, nblocks, nullptr);
+            fa.join();
+            fb.join();
+            k.stop();
+            return n;
+        }
+        case 2: { stream<stereo_t> s; StereoToMono k(&s); return run1(&s, k, &k.out, in0, blocks, nblocks, out0); }
+        case 3: {
+            stream<stereo_t> s;
+            StereoToChannels k(&s);
+            k.start();
+            std::thread f([&] { feed(&s, (const stereo_t*)in0, blocks, nblocks); });
+            long long n = 0;
+            for (int b = 0; b < nblocks; b++) {   // out_left and out_right are swapped one after the other (audio.h:176-177)
+                int c = k.out_left.read();
+                if (c < 0) break;
+                memcpy(out0 + n, k.out_left.readBuf, (size_t)c * sizeof(float));
+                k.out_left.flush();
+                int c2 = k.out_right.read();
+                if (c2 < 0) break;
+                memcpy(out1 + n, k.out_right.readBuf, (size_t)c2 * sizeof(float));
+                k.out_right.flush();
+                n += c;
+            }
+            f.join();
+            k.stop();
+            return n;
+        }
+        case 4: { stream<complex_t> s; ComplexToStereo k(&s); return run1(&s, k, &k.out, in0, blocks, nblocks, out0); }
+        case 5: { stream<complex_t> s; ComplexToReal k(&s); return run1(&s, k, &k.out, in0, blocks, nblocks, out0); }
+        case 6: { stream<complex_t> s; ComplexToImag k(&s); return run1(&s, k, &k.out, in0, blocks, nblocks, out0); }
+        case 7: { stream<float> s; RealToComplex k(&s); return run1(&s, k, &k.out, in0, blocks, nblocks, out0); }
+    }
+    return -1;
+}
+// Volume<T>: processing.h:348-421. call_set: whether setVolume(volume) is called after construction
+long long ref_volume(int dtype, float volume, int call_set, int muted, const float* in, const int* blocks, int nblocks, float* out) {
+    if (dtype == 1) {
+        stream<stereo_t> s;
+        Volume<stereo_t> k(&s, volume);
+        if (call_set) k.setVolume(volume);
+        k.setMuted(muted != 0);
+        return run1(&s, k, &k.out, in, blocks, nblocks, out);
+    }
+    stream<float> s;
+    Volume<float> k(&s, volume);
+    if (call_set) k.setVolume(volume);
+    k.setMuted(muted != 0);
+    return run1(&s, k, &k.out, in, blocks, nblocks, out);
+}
+long long ref_threshold(const float* in, const int* blocks, int nblocks, unsigned char* out) {
+    stream<float> s;
+    Threshold k(&s);
+    return run1(&s, k, &k.out, in, blocks, nblocks, out);
+}
+long long ref_delay_imag(const float* in, const int* blocks, int nblocks, float* out) {
+    stream<complex_t> s;
+    DelayImag k(&s);
+    return run1(&s, k, &k.out, in, blocks, nblocks, out);
+}
+long long ref_amdemod(const float* in, const int* blocks, int nblocks, float* out) {
+    stream<complex_t> s;
+    AMDemod k(&s);
+    return run1(&s, k, &k.out, in, blocks, nblocks, out);
+}
+long long ref_squelch(float level, const float* in, const int* blocks, int nblocks, float* out) {
+    stream<complex_t> s;
+    Squelch k(&s, level);
+    return run1(&s, k, &k.out, in, blocks, nblocks, out);
+}
+long long ref_ssbdemod(float sampleRate, float bandWidth, int mode, const float* in, const int* blocks, int nblocks,
+                       float* out) {
+    stream<complex_t> s;
+    SSBDemod k(&s, sampleRate, bandWidth, mode);
+    return run1(&s, k, &k.out, in, blocks, nblocks, out);
 }
 
 }  // extern "C"

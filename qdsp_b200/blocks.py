@@ -696,3 +696,270 @@ class CostasLoop(_Block):
 
 
 __all__ = [n for n in dir() if not n.startswith("_")]
+
+
+# ---------------------------------------------------------------------------------------------
+# element-wise / layout / per-block-statistic blocks (reference math.h, audio.h, convertion.h,
+# processing.h Volume / DelayImag / Squelch / Threshold, demodulator.h AMDemod / SSBDemod)
+# stereo_t streams are viewed as complex64 (l = re, r = im), like everywhere else in this module.
+# ---------------------------------------------------------------------------------------------
+MATH_ADD, MATH_SUB, MATH_MUL = 0, 1, 2
+(LAYOUT_MONO_TO_STEREO, LAYOUT_CHANNELS_TO_STEREO, LAYOUT_STEREO_TO_MONO, LAYOUT_STEREO_TO_CHANNELS,
+ LAYOUT_COMPLEX_TO_STEREO, LAYOUT_COMPLEX_TO_REAL, LAYOUT_COMPLEX_TO_IMAG, LAYOUT_REAL_TO_COMPLEX) = range(8)
+
+
+class _Binary:
+    """Two-input block (math.h): process(a, b) -> out. Mismatched lengths produce nothing, like the reference's
+    `if (a_count != b_count) { flush; return 0; }` (math.h:26-30)."""
+
+    _op = MATH_ADD
+
+    def __init__(self, dtype=np.complex64):
+        _lib.require_device()
+        self.dtype = np.dtype(dtype)
+        self._code = CF32 if self.dtype == np.complex64 else F32
+        self.stream = None
+
+    def process_device(self, a_ptr, b_ptr, out_ptr, n, stream=None) -> int:
+        return int(check(_L().qdsp_math_process(self._op, self._code, a_ptr, b_ptr, out_ptr, int(n), stream), type(self).__name__))
+
+    def process(self, a, b) -> np.ndarray:
+        a = np.ascontiguousarray(a, dtype=self.dtype)
+        b = np.ascontiguousarray(b, dtype=self.dtype)
+        if len(a) != len(b):
+            return np.empty(0, self.dtype)
+        da, db = DevBuf.from_numpy(a), DevBuf.from_numpy(b)
+        do = DevBuf(max(a.nbytes, 16))
+        m = self.process_device(da.ptr, db.ptr, do.ptr, len(a))
+        y = do.to_numpy(self.dtype, m)
+        for d in (da, db, do):
+            d.free()
+        return y
+
+
+class Add(_Binary):
+    """dsp::Add<T>: init(a, b)."""
+    _op = MATH_ADD
+
+
+class Substract(_Binary):
+    """dsp::Substract<T> (sic): init(a, b)."""
+    _op = MATH_SUB
+
+
+class Multiply(_Binary):
+    """dsp::Multiply<T>: init(a, b); complex product for complex_t."""
+    _op = MATH_MUL
+
+
+class _Layout(_Block):
+    _op = 0
+
+    def __init__(self):
+        super().__init__()
+        _lib.require_device()
+
+    def _run(self, in_ptr, out_ptr, n, block):
+        return _L().qdsp_layout_process(self._op, in_ptr, None, out_ptr, None, n, self.stream)
+
+
+class MonoToStereo(_Layout):
+    """dsp::MonoToStereo (audio.h:5-42)."""
+    _op, in_dtype, out_dtype = LAYOUT_MONO_TO_STEREO, np.float32, np.complex64
+
+
+class StereoToMono(_Layout):
+    """dsp::StereoToMono (audio.h:96-145)."""
+    _op, in_dtype, out_dtype = LAYOUT_STEREO_TO_MONO, np.complex64, np.float32
+
+
+class ComplexToStereo(_Layout):
+    """dsp::ComplexToStereo (convertion.h:5-44)."""
+    _op, in_dtype, out_dtype = LAYOUT_COMPLEX_TO_STEREO, np.complex64, np.complex64
+
+
+class ComplexToReal(_Layout):
+    """dsp::ComplexToReal (convertion.h:46-83)."""
+    _op, in_dtype, out_dtype = LAYOUT_COMPLEX_TO_REAL, np.complex64, np.float32
+
+
+class ComplexToImag(_Layout):
+    """dsp::ComplexToImag (convertion.h:85-122)."""
+    _op, in_dtype, out_dtype = LAYOUT_COMPLEX_TO_IMAG, np.complex64, np.float32
+
+
+class RealToComplex(_Layout):
+    """dsp::RealToComplex (convertion.h:125-170)."""
+    _op, in_dtype, out_dtype = LAYOUT_REAL_TO_COMPLEX, np.float32, np.complex64
+
+
+class ChannelsToStereo:
+    """dsp::ChannelsToStereo (audio.h:44-94): process(left, right) -> stereo_t."""
+
+    def __init__(self):
+        _lib.require_device()
+
+    def process(self, left, right) -> np.ndarray:
+        left = np.ascontiguousarray(left, np.float32)
+        right = np.ascontiguousarray(right, np.float32)
+        n = len(left)   # the reference interleaves count_l elements whatever count_r is (audio.h:76-80)
+        dl, dr, do = DevBuf.from_numpy(left), DevBuf.from_numpy(right), DevBuf(max(n * 8, 16))
+        m = int(check(_L().qdsp_layout_process(LAYOUT_CHANNELS_TO_STEREO, dl.ptr, dr.ptr, do.ptr, None, n, None)))
+        y = do.to_numpy(np.complex64, m)
+        for d in (dl, dr, do):
+            d.free()
+        return y
+
+
+class StereoToChannels:
+    """dsp::StereoToChannels (audio.h:147-187): process(stereo) -> (left, right)."""
+
+    def __init__(self):
+        _lib.require_device()
+
+    def process(self, x):
+        x = np.ascontiguousarray(x, np.complex64)
+        n = len(x)
+        di, dl, dr = DevBuf.from_numpy(x), DevBuf(max(n * 4, 16)), DevBuf(max(n * 4, 16))
+        m = int(check(_L().qdsp_layout_process(LAYOUT_STEREO_TO_CHANNELS, di.ptr, None, dl.ptr, dr.ptr, n, None)))
+        out = dl.to_numpy(np.float32, m), dr.to_numpy(np.float32, m)
+        for d in (di, dl, dr):
+            d.free()
+        return out
+
+
+class Volume(_Block):
+    """dsp::Volume<T>: init(in, volume). As in the reference, the constructor stores `volume` but leaves the applied
+    level at 1.0 until setVolume() is called (processing.h:355-359 vs :371-374)."""
+
+    def __init__(self, volume: float = 1.0, dtype=np.float32):
+        super().__init__()
+        _lib.require_device()
+        self.in_dtype = self.out_dtype = np.dtype(dtype)
+        self._code = CF32 if self.in_dtype == np.complex64 else F32
+        self._volume, self._level, self._muted = float(volume), 1.0, False
+
+    def setVolume(self, volume):  # noqa: N802
+        self._volume = float(volume)
+        self._level = float(_L().qdsp_volume_level(self._volume))
+
+    def getVolume(self):  # noqa: N802
+        return self._volume
+
+    def setMuted(self, muted):  # noqa: N802
+        self._muted = bool(muted)
+
+    def getMuted(self):  # noqa: N802
+        return self._muted
+
+    def _run(self, in_ptr, out_ptr, n, block):
+        return _L().qdsp_volume_process(self._code, self._level, int(self._muted), in_ptr, out_ptr, n, self.stream)
+
+
+class Threshold(_Block):
+    """dsp::Threshold (processing.h:554-610): uint8 stream of (x > 0)."""
+    in_dtype, out_dtype = np.float32, np.uint8
+
+    def __init__(self):
+        super().__init__()
+        _lib.require_device()
+
+    def _run(self, in_ptr, out_ptr, n, block):
+        return _L().qdsp_threshold_process(in_ptr, out_ptr, n, self.stream)
+
+
+class DelayImag(_Block):
+    """dsp::DelayImag (processing.h:300-346)."""
+    _destroy = "qdsp_delayimag_destroy"
+
+    def __init__(self):
+        super().__init__()
+        _lib.require_device()
+        self.h = check(_L().qdsp_delayimag_create(), "qdsp_delayimag_create")
+
+    def get_state(self) -> float:
+        v = C.c_float()
+        check(_L().qdsp_delayimag_get_state(self.h, C.byref(v)))
+        return v.value
+
+    def _run(self, in_ptr, out_ptr, n, block):
+        return _L().qdsp_delayimag_process(self.h, in_ptr, out_ptr, n, self.stream)
+
+
+class AMDemod(_Block):
+    """dsp::AMDemod (demodulator.h:332-378): |x| minus its mean over the run() block."""
+    _destroy = "qdsp_amdemod_destroy"
+    out_dtype = np.float32
+
+    def __init__(self):
+        super().__init__()
+        _lib.require_device()
+        self.h = check(_L().qdsp_amdemod_create(), "qdsp_amdemod_create")
+
+    def _run(self, in_ptr, out_ptr, n, block):
+        b, nb, bs = _blocks_arg(n, block)
+        return _L().qdsp_amdemod_process(self.h, in_ptr, out_ptr, n, _iptr(b), nb, bs, self.stream)
+
+
+class Squelch(_Block):
+    """dsp::Squelch: init(in, level) (processing.h:424-489)."""
+    _destroy = "qdsp_squelch_destroy"
+
+    def __init__(self, level: float = -50.0):
+        super().__init__()
+        _lib.require_device()
+        self.h = check(_L().qdsp_squelch_create(float(level)), "qdsp_squelch_create")
+
+    def setLevel(self, level):  # noqa: N802
+        _L().qdsp_squelch_set_level(self.h, float(level))
+
+    def getLevel(self):  # noqa: N802
+        return float(_L().qdsp_squelch_get_level(self.h))
+
+    def _run(self, in_ptr, out_ptr, n, block):
+        b, nb, bs = _blocks_arg(n, block)
+        return _L().qdsp_squelch_process(self.h, in_ptr, out_ptr, n, _iptr(b), nb, bs, self.stream)
+
+
+class SSBDemod(_Block):
+    """dsp::SSBDemod: init(in, sampleRate, bandWidth, mode) (demodulator.h:380-497)."""
+    _destroy = "qdsp_ssbdemod_destroy"
+    out_dtype = np.float32
+    MODE_USB, MODE_LSB, MODE_DSB = 0, 1, 2
+
+    def __init__(self, sampleRate: float, bandWidth: float, mode: int):
+        super().__init__()
+        _lib.require_device()
+        self._sampleRate, self._bandWidth, self._mode = float(sampleRate), float(bandWidth), int(mode)
+        self.h = check(_L().qdsp_ssbdemod_create(self._sampleRate, self._bandWidth, self._mode), "qdsp_ssbdemod_create")
+
+    def _reconf(self):
+        _L().qdsp_ssbdemod_configure(self.h, self._sampleRate, self._bandWidth, self._mode)
+
+    def setSampleRate(self, v):  # noqa: N802
+        self._sampleRate = float(v)
+        self._reconf()
+
+    def setBandWidth(self, v):  # noqa: N802
+        self._bandWidth = float(v)
+        self._reconf()
+
+    def setMode(self, v):  # noqa: N802
+        self._mode = int(v)
+        self._reconf()
+
+    def phase_delta(self) -> complex:
+        re, im = C.c_float(), C.c_float()
+        _L().qdsp_ssbdemod_get_phase_delta(self.h, C.byref(re), C.byref(im))
+        return complex(re.value, im.value)
+
+    def get_phase(self) -> complex:
+        re, im = C.c_float(), C.c_float()
+        _L().qdsp_ssbdemod_get_phase(self.h, C.byref(re), C.byref(im))
+        return complex(re.value, im.value)
+
+    def set_phase(self, p: complex):
+        _L().qdsp_ssbdemod_set_phase(self.h, float(p.real), float(p.imag))
+
+    def _run(self, in_ptr, out_ptr, n, block):
+        return _L().qdsp_ssbdemod_process(self.h, in_ptr, out_ptr, n, self.stream)

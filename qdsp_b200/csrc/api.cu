@@ -986,3 +986,188 @@ int qdsp_synth_fm_cf32(void* out_dev, long long start, long long count, long lon
 double qdsp_measure_fp32_peak(int packed, int iters) { return run_fp32_peak(packed, iters); }
 
 }  // extern "C"
+
+// =================================================================================================
+// element-wise / layout / per-block-statistic blocks ("next" rows): math.h, audio.h, convertion.h,
+// processing.h Volume / DelayImag / Squelch / Threshold, demodulator.h AMDemod / SSBDemod
+// =================================================================================================
+struct qdsp_delayimag {
+    DevState st;  // [2] ping-pong lastIm
+    int cur = 0;
+};
+struct qdsp_amdemod {
+    Partition part;
+    Scratch scratch;
+};
+struct qdsp_squelch {
+    float level = -50.0f;  // processing.h:486
+    Partition part;
+    Scratch scratch;
+};
+struct qdsp_ssbdemod {
+    Nco nco;
+    float2 inc_pow[3];
+    void configure(float sampleRate, float bandWidth, int mode) {
+        // demodulator.h:403-412: float expressions, std::cos / std::sin float overloads
+        float re = 1.0f, im = 0.0f;
+        if (mode == QDSP_SSB_USB) {
+            re = cosf((bandWidth / sampleRate) * QDSP_FL_M_PI);
+            im = sinf((bandWidth / sampleRate) * QDSP_FL_M_PI);
+        } else if (mode == QDSP_SSB_LSB) {
+            re = cosf(-(bandWidth / sampleRate) * QDSP_FL_M_PI);
+            im = sinf(-(bandWidth / sampleRate) * QDSP_FL_M_PI);
+        }
+        nco.set_inc(re, im);
+        const double th = atan2((double)im, (double)re);
+        for (int j = 1; j <= 3; j++) inc_pow[j - 1] = make_float2((float)cos(th * j), (float)sin(th * j));
+    }
+};
+
+extern "C" {
+
+long long qdsp_math_process(int op, int dtype, const void* a_dev, const void* b_dev, void* out_dev, long long count,
+                            qdsp_stream_t s) {
+    if (count < 0) return -1;
+    // math.h:32-37, 79-84, 126-131: complex/stereo add and subtract are float add/subtract over 2*count floats;
+    // only Multiply<complex_t> is a complex product
+    const long long nf = dtype == QDSP_CF32 ? 2 * count : count;
+    if (launch_math(op, dtype == QDSP_CF32, (const float*)a_dev, (const float*)b_dev, (float*)out_dev, nf, as_stream(s)) != 0)
+        return -1;
+    return count;
+}
+
+long long qdsp_layout_process(int op, const void* in0_dev, const void* in1_dev, void* out0_dev, void* out1_dev,
+                              long long count, qdsp_stream_t s_) {
+    if (count < 0) return -1;
+    cudaStream_t s = as_stream(s_);
+    const float* i0 = (const float*)in0_dev;
+    const float* i1 = (const float*)in1_dev;
+    float* o0 = (float*)out0_dev;
+    float* o1 = (float*)out1_dev;
+    int rc = 0;
+    switch (op) {
+        case QDSP_LAYOUT_MONO_TO_STEREO: rc = launch_layout(0, i0, i0, o0, nullptr, count, s); break;        // audio.h:30
+        case QDSP_LAYOUT_CHANNELS_TO_STEREO: rc = launch_layout(0, i0, i1, o0, nullptr, count, s); break;    // audio.h:80
+        case QDSP_LAYOUT_STEREO_TO_MONO: rc = launch_layout(1, i0, nullptr, o0, nullptr, count, s); break;   // audio.h:129-131
+        case QDSP_LAYOUT_STEREO_TO_CHANNELS: rc = launch_layout(2, i0, nullptr, o0, o1, count, s); break;    // audio.h:173
+        case QDSP_LAYOUT_COMPLEX_TO_STEREO:                                                                  // convertion.h:32
+            if (count > 0 && cudaMemcpyAsync(o0, i0, (size_t)count * 8, cudaMemcpyDeviceToDevice, s) != cudaSuccess) {
+                set_last_error("layout: device copy failed");
+                rc = -1;
+            }
+            break;
+        case QDSP_LAYOUT_COMPLEX_TO_REAL: rc = launch_layout(2, i0, nullptr, o0, nullptr, count, s); break;  // convertion.h:71
+        case QDSP_LAYOUT_COMPLEX_TO_IMAG: rc = launch_layout(2, i0, nullptr, nullptr, o0, count, s); break;  // convertion.h:110
+        case QDSP_LAYOUT_REAL_TO_COMPLEX: rc = launch_layout(0, i0, nullptr, o0, nullptr, count, s); break;  // convertion.h:157
+        default:
+            set_last_error("layout: unknown op %d", op);
+            rc = -1;
+    }
+    return rc == 0 ? count : -1;
+}
+
+float qdsp_volume_level(float volume) { return powf(volume, 2); }   // Volume::setVolume, processing.h:373-374
+long long qdsp_volume_process(int dtype, float level, int muted, const void* in_dev, void* out_dev, long long count,
+                              qdsp_stream_t s) {
+    if (count < 0) return -1;
+    const long long nf = dtype == QDSP_CF32 ? 2 * count : count;
+    if (muted) {   // processing.h:392-399
+        if (count > 0 && cudaMemsetAsync(out_dev, 0, (size_t)nf * 4, as_stream(s)) != cudaSuccess) {
+            set_last_error("volume: memset failed");
+            return -1;
+        }
+        return count;
+    }
+    if (launch_scale((const float*)in_dev, (float*)out_dev, nf, level, as_stream(s)) != 0) return -1;
+    return count;
+}
+
+long long qdsp_threshold_process(const float* in_dev, unsigned char* out_dev, long long count, qdsp_stream_t s) {
+    if (count < 0) return -1;
+    if (launch_threshold(in_dev, out_dev, count, as_stream(s)) != 0) return -1;
+    return count;
+}
+
+qdsp_delayimag* qdsp_delayimag_create(void) {
+    qdsp_delayimag* h = new (std::nothrow) qdsp_delayimag();
+    if (!h) return nullptr;
+    const float z[2] = {0.0f, 0.0f};   // lastIm = 0, processing.h:343
+    if (h->st.init(2, z) != 0) {
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+void qdsp_delayimag_destroy(qdsp_delayimag* h) { delete h; }
+long long qdsp_delayimag_process(qdsp_delayimag* h, const void* in_dev, void* out_dev, long long count, qdsp_stream_t s) {
+    if (count < 0) return -1;
+    if (count == 0) return 0;
+    if (launch_delay_imag((const float2*)in_dev, (float2*)out_dev, count, h->st.p + h->cur, h->st.p + (h->cur ^ 1),
+                          as_stream(s)) != 0)
+        return -1;
+    h->cur ^= 1;
+    return count;
+}
+int qdsp_delayimag_get_state(qdsp_delayimag* h, float* lastIm) { return h->st.get(lastIm, 1, h->cur); }
+int qdsp_delayimag_set_state(qdsp_delayimag* h, float lastIm) { return h->st.set(&lastIm, 1, h->cur); }
+
+qdsp_amdemod* qdsp_amdemod_create(void) { return new (std::nothrow) qdsp_amdemod(); }
+void qdsp_amdemod_destroy(qdsp_amdemod* h) { delete h; }
+long long qdsp_amdemod_process(qdsp_amdemod* h, const void* in_dev, float* out_dev, long long count, const int* blocks,
+                               int nblocks, int block_size, qdsp_stream_t s_) {
+    cudaStream_t s = as_stream(s_);
+    if (h->part.build(count, blocks, nblocks, block_size, 1, 1, s) != 0) return -1;
+    const int nb = h->part.view.nblocks;
+    if (nb == 0) return 0;
+    if (h->scratch.reserve(mag_scratch_bytes(nb)) != 0) return -1;
+    if (launch_amdemod((const float2*)in_dev, out_dev, h->part, (double*)h->scratch.p, s) != 0) return -1;
+    return count;
+}
+
+qdsp_squelch* qdsp_squelch_create(float level) {
+    qdsp_squelch* h = new (std::nothrow) qdsp_squelch();
+    if (h) h->level = level;
+    return h;
+}
+void qdsp_squelch_destroy(qdsp_squelch* h) { delete h; }
+void qdsp_squelch_set_level(qdsp_squelch* h, float level) { h->level = level; }
+float qdsp_squelch_get_level(qdsp_squelch* h) { return h->level; }
+long long qdsp_squelch_process(qdsp_squelch* h, const void* in_dev, void* out_dev, long long count, const int* blocks,
+                               int nblocks, int block_size, qdsp_stream_t s_) {
+    cudaStream_t s = as_stream(s_);
+    if (h->part.build(count, blocks, nblocks, block_size, 1, 1, s) != 0) return -1;
+    const int nb = h->part.view.nblocks;
+    if (nb == 0) return 0;
+    if (h->scratch.reserve(mag_scratch_bytes(nb)) != 0) return -1;
+    if (launch_squelch((const float2*)in_dev, (float2*)out_dev, h->part, (double*)h->scratch.p, h->level, s) != 0) return -1;
+    return count;
+}
+
+qdsp_ssbdemod* qdsp_ssbdemod_create(float sampleRate, float bandWidth, int mode) {
+    qdsp_ssbdemod* h = new (std::nothrow) qdsp_ssbdemod();
+    if (!h) return nullptr;
+    h->configure(sampleRate, bandWidth, mode);
+    h->nco.phase = 0;   // phase = (1, 0), demodulator.h:401
+    return h;
+}
+void qdsp_ssbdemod_destroy(qdsp_ssbdemod* h) { delete h; }
+int qdsp_ssbdemod_configure(qdsp_ssbdemod* h, float sampleRate, float bandWidth, int mode) {
+    h->configure(sampleRate, bandWidth, mode);
+    return 0;
+}
+void qdsp_ssbdemod_get_phase_delta(qdsp_ssbdemod* h, float* re, float* im) {
+    *re = h->nco.inc_re;
+    *im = h->nco.inc_im;
+}
+void qdsp_ssbdemod_get_phase(qdsp_ssbdemod* h, float* re, float* im) { h->nco.get_phase(re, im); }
+void qdsp_ssbdemod_set_phase(qdsp_ssbdemod* h, float re, float im) { h->nco.set_phase(re, im); }
+long long qdsp_ssbdemod_process(qdsp_ssbdemod* h, const void* in_dev, float* out_dev, long long count, qdsp_stream_t s) {
+    if (count < 0) return -1;
+    if (launch_ssb((const float2*)in_dev, out_dev, count, h->nco.phase, h->nco.step, h->inc_pow[0], h->inc_pow[1],
+                   h->inc_pow[2], as_stream(s)) != 0)
+        return -1;
+    h->nco.advance(count);
+    return count;
+}
+
+}  // extern "C"

@@ -120,6 +120,7 @@ struct Nco {
     uint64_t step = 0;                    // theta in turns * 2^64
     uint64_t phase = 0;                   // current phase in turns * 2^64
     void set_freq(float sampleRate, float freq);
+    void set_inc(float re, float im);     // any other float32 phasor increment (SSBDemod, demodulator.h:403-412)
     void set_phase(float re, float im);
     void get_phase(float* re, float* im) const;
     void advance(long long n) { phase += step * (uint64_t)n; }

@@ -72,4 +72,17 @@ int launch_costas(const float2* in, float2* out, long long count, int order, flo
 size_t scan_scratch_bytes(long long count);
 size_t costas_scratch_bytes(long long count, int chunk);
 
+// ---- k_pointwise.cu: element-wise / layout / per-block-statistic blocks ---------------------------
+int launch_math(int op, int complex_mul, const float* a, const float* b, float* out, long long nfloats, cudaStream_t s);
+int launch_layout(int mode, const float* in0, const float* in1, float* out0, float* out1, long long count, cudaStream_t s);
+int launch_scale(const float* in, float* out, long long nfloats, float level, cudaStream_t s);
+int launch_threshold(const float* in, unsigned char* out, long long n, cudaStream_t s);
+int launch_delay_imag(const float2* in, float2* out, long long count, const float* state_in, float* state_out,
+                      cudaStream_t s);
+size_t mag_scratch_bytes(int nblocks);
+int launch_amdemod(const float2* in, float* out, const Partition& part, double* partial, cudaStream_t s);
+int launch_squelch(const float2* in, float2* out, const Partition& part, double* partial, float level, cudaStream_t s);
+int launch_ssb(const float2* in, float* out, long long count, uint64_t phase0, uint64_t step, float2 inc1, float2 inc2,
+               float2 inc3, cudaStream_t s);
+
 }  // namespace qdsp

@@ -165,6 +165,11 @@ void Nco::set_freq(float sampleRate, float freq) {
     inc_im = sinf(a);
     step = turns_from_angle(atan2((double)inc_im, (double)inc_re));
 }
+void Nco::set_inc(float re, float im) {
+    inc_re = re;
+    inc_im = im;
+    step = turns_from_angle(atan2((double)im, (double)re));
+}
 void Nco::set_phase(float re, float im) { phase = turns_from_angle(atan2((double)im, (double)re)); }
 void Nco::get_phase(float* re, float* im) const {
     const double ang = (double)(int64_t)phase * (kTwoPi / 18446744073709551616.0);

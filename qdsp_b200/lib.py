@@ -140,6 +140,31 @@ SIGNATURES = {
     "qdsp_costas_set_state": (_i, [_vp, _fp]),
     "qdsp_costas_set_chunking": (_i, [_vp, _i, _i]),
     "qdsp_costas_last_residual": (_f, [_vp]),
+    "qdsp_math_process": (_ll, [_i, _i, _vp, _vp, _vp, _ll, _vp]),
+    "qdsp_layout_process": (_ll, [_i, _vp, _vp, _vp, _vp, _ll, _vp]),
+    "qdsp_volume_level": (_f, [_f]),
+    "qdsp_volume_process": (_ll, [_i, _f, _i, _vp, _vp, _ll, _vp]),
+    "qdsp_threshold_process": (_ll, [_vp, _vp, _ll, _vp]),
+    "qdsp_delayimag_create": (_vp, []),
+    "qdsp_delayimag_destroy": (None, [_vp]),
+    "qdsp_delayimag_process": (_ll, [_vp, _vp, _vp, _ll, _vp]),
+    "qdsp_delayimag_get_state": (_i, [_vp, _fp]),
+    "qdsp_delayimag_set_state": (_i, [_vp, _f]),
+    "qdsp_amdemod_create": (_vp, []),
+    "qdsp_amdemod_destroy": (None, [_vp]),
+    "qdsp_amdemod_process": (_ll, [_vp, _vp, _vp, _ll, _ip, _i, _i, _vp]),
+    "qdsp_squelch_create": (_vp, [_f]),
+    "qdsp_squelch_destroy": (None, [_vp]),
+    "qdsp_squelch_set_level": (None, [_vp, _f]),
+    "qdsp_squelch_get_level": (_f, [_vp]),
+    "qdsp_squelch_process": (_ll, [_vp, _vp, _vp, _ll, _ip, _i, _i, _vp]),
+    "qdsp_ssbdemod_create": (_vp, [_f, _f, _i]),
+    "qdsp_ssbdemod_destroy": (None, [_vp]),
+    "qdsp_ssbdemod_configure": (_i, [_vp, _f, _f, _i]),
+    "qdsp_ssbdemod_get_phase_delta": (None, [_vp, _fp, _fp]),
+    "qdsp_ssbdemod_get_phase": (None, [_vp, _fp, _fp]),
+    "qdsp_ssbdemod_set_phase": (None, [_vp, _f, _f]),
+    "qdsp_ssbdemod_process": (_ll, [_vp, _vp, _vp, _ll, _vp]),
     "qdsp_synth_uniform_cf32": (_i, [_vp, _ull, _ll, _ll, _vp]),
     "qdsp_synth_fm_cf32": (_i, [_vp, _ll, _ll, _ll, _ll, _ll, _d, _d, _d, _ull, _vp]),
     "qdsp_measure_fp32_peak": (_d, [_i, _i]),

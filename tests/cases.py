@@ -41,11 +41,35 @@ CASES = {
     "costas4": dict(kind="costas", order=4, bw=0.004, src=("qpsk", 23, 0, 8000), block=4000),
     "costas2": dict(kind="costas", order=2, bw=0.004, src=("bpsk", 24, 0, 8000), block=4000),
     "costas8": dict(kind="costas", order=8, bw=0.004, src=("qpsk", 25, 0, 4000), block=4000),
+    # ---- "next" rows: element-wise / layout / per-block-statistic blocks (math.h, audio.h, convertion.h, processing.h,
+    # demodulator.h). Two-input blocks take their second stream from `src2`.
+    "math_cf32": dict(kind="math", src=("uniform", 31, 0, 2000), src2=("uniform", 32, 0, 2000), block=[1000, 3, 997]),
+    "math_f32": dict(kind="math", src=("uniform_f32", 33, 0, 2001), src2=("uniform_f32", 34, 0, 2001), block=667),
+    "mono_to_stereo": dict(kind="layout", op=0, src=("uniform_f32", 35, 0, 1500), block=[1000, 500]),
+    "channels_to_stereo": dict(kind="layout", op=1, src=("uniform_f32", 36, 0, 1500), src2=("uniform_f32", 37, 0, 1500), block=[1, 1499]),
+    "stereo_to_mono": dict(kind="layout", op=2, src=("uniform", 38, 0, 1500), block=500),
+    "stereo_to_channels": dict(kind="layout", op=3, src=("uniform", 39, 0, 1500), block=[700, 800]),
+    "complex_to_stereo": dict(kind="layout", op=4, src=("uniform", 40, 0, 1000), block=1000),
+    "complex_to_real": dict(kind="layout", op=5, src=("uniform", 41, 0, 1501), block=[1000, 501]),
+    "complex_to_imag": dict(kind="layout", op=6, src=("uniform", 42, 0, 1501), block=[1000, 501]),
+    "real_to_complex": dict(kind="layout", op=7, src=("uniform_f32", 43, 0, 1500), block=[1000, 500]),
+    "volume_f32": dict(kind="volume", volume=0.7, call_set=1, muted=0, src=("uniform_f32", 44, 0, 2002), block=[1001, 1001]),
+    # the reference's init() stores the volume but leaves the applied level at 1.0 (processing.h:355-359)
+    "volume_stereo_noset": dict(kind="volume", volume=0.7, call_set=0, muted=0, src=("uniform", 45, 0, 1000), block=1000),
+    "volume_muted": dict(kind="volume", volume=0.7, call_set=1, muted=1, src=("uniform", 46, 0, 1000), block=500),
+    "threshold": dict(kind="threshold", src=("uniform_f32", 47, 0, 2000), block=[1999, 1]),
+    "delay_imag": dict(kind="delay_imag", src=("uniform", 48, 0, 2000), block=[1000, 1, 999]),
+    "amdemod": dict(kind="amdemod", src=("qpsk_am", 49, 0, 9000), block=[4000, 1000, 4000]),
+    # three run() blocks at about -1 dB, -61 dB and -27 dB mean magnitude against a -30 dB gate: pass, mute, pass
+    "squelch": dict(kind="squelch", level=-30.0, src=("uniform_steps", 50, [1000, 500, 1500], [1.0, 0.001, 0.05]), block=[1000, 500, 1500]),
+    "ssb_usb": dict(kind="ssb", fs=48e3, bw=3e3, mode=0, src=("uniform", 51, 0, 3000), block=[1000, 777, 1223]),
+    "ssb_lsb": dict(kind="ssb", fs=48e3, bw=3e3, mode=1, src=("uniform", 52, 0, 3000), block=3000),
+    "ssb_dsb": dict(kind="ssb", fs=48e3, bw=3e3, mode=2, src=("uniform", 53, 0, 1000), block=[600, 400]),
 }
 
 
-def make_input(c) -> np.ndarray:
-    src = c["src"]
+def make_input(c, key="src") -> np.ndarray:
+    src = c[key]
     k = src[0]
     if k == "uniform":
         return synth.uniform_cf32(src[1], src[2], src[3])
@@ -63,6 +87,11 @@ def make_input(c) -> np.ndarray:
         return synth.qpsk_cf32(src[1], src[2], src[3])
     if k == "bpsk":
         return synth.bpsk_cf32(src[1], src[2], src[3])
+    if k == "uniform_steps":  # uniform noise scaled per run() block
+        sizes, gains = src[2], src[3]
+        x = synth.uniform_cf32(src[1], 0, int(sum(sizes)))
+        g = np.repeat(np.asarray(gains, np.float32), sizes)
+        return (x * g).astype(np.complex64)
     if k == "qpsk_am":
         return synth.qpsk_cf32(src[1], src[2], src[3], am_depth=0.5, am_period=3000)
     raise ValueError(k)

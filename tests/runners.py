@@ -2,6 +2,7 @@
 import numpy as np
 
 from oracle import loader
+from tests.cases import make_input
 
 
 def _stereo(x):
@@ -56,6 +57,25 @@ def run_port(c, x):
         return P.ff_agc(x), None
     if k == "costas":
         return P.costas(c["order"], c["bw"], x)[0], None
+    if k == "math":
+        x2 = make_input(c, "src2")
+        return np.stack([P.math(op, x, x2) for op in range(3)]), None
+    if k == "layout":
+        x2 = make_input(c, "src2") if "src2" in c else None
+        y = P.layout(c["op"], x, x2)
+        return (np.stack(y) if c["op"] == 3 else y), None
+    if k == "volume":
+        return P.volume(x, c["volume"], c["call_set"], c["muted"]), None
+    if k == "threshold":
+        return P.threshold(x), None
+    if k == "delay_imag":
+        return P.delay_imag(x), None
+    if k == "amdemod":
+        return P.amdemod(x, c["block"]), None
+    if k == "squelch":
+        return P.squelch(c["level"], x, c["block"]), None
+    if k == "ssb":
+        return P.ssbdemod(c["fs"], c["bw"], c["mode"], x, c["block"]), None
     raise ValueError(k)
 
 
@@ -157,6 +177,64 @@ def run_gpu(c, x, variant=0):
             outs.append(g.process(x[off:off + s]))
             off += s
         return np.concatenate(outs), None
+    if k == "math":
+        x2 = make_input(c, "src2")
+        outs = []
+        for cls in (B.Add, B.Substract, B.Multiply):
+            blk, off, parts = cls(x.dtype), 0, []
+            for s in loader.as_blocks(len(x), c["block"]):
+                parts.append(blk.process(x[off:off + s], x2[off:off + s]))
+                off += s
+            outs.append(np.concatenate(parts))
+        return np.stack(outs), None
+    if k == "layout":
+        op = c["op"]
+        sizes = loader.as_blocks(len(x), c["block"])
+        if op == 1:
+            x2 = make_input(c, "src2")
+            blk, off, parts = B.ChannelsToStereo(), 0, []
+            for s in sizes:
+                parts.append(blk.process(x[off:off + s], x2[off:off + s]))
+                off += s
+            return np.concatenate(parts), None
+        if op == 3:
+            blk, off, ls, rs = B.StereoToChannels(), 0, [], []
+            for s in sizes:
+                l, r = blk.process(x[off:off + s])
+                ls.append(l)
+                rs.append(r)
+                off += s
+            return np.stack([np.concatenate(ls), np.concatenate(rs)]), None
+        blk = {0: B.MonoToStereo, 2: B.StereoToMono, 4: B.ComplexToStereo, 5: B.ComplexToReal, 6: B.ComplexToImag,
+               7: B.RealToComplex}[op]()
+        off, parts = 0, []
+        for s in sizes:
+            parts.append(blk.process(x[off:off + s]))
+            off += s
+        return np.concatenate(parts), None
+    if k in ("volume", "threshold", "delay_imag"):
+        if k == "volume":
+            blk = B.Volume(c["volume"], x.dtype)
+            if c["call_set"]:
+                blk.setVolume(c["volume"])
+            blk.setMuted(bool(c["muted"]))
+        else:
+            blk = B.Threshold() if k == "threshold" else B.DelayImag()
+        off, parts = 0, []
+        for s in loader.as_blocks(len(x), c["block"]):
+            parts.append(blk.process(x[off:off + s]))
+            off += s
+        return np.concatenate(parts), None
+    if k == "amdemod":
+        return B.AMDemod().process(x, c["block"]), None
+    if k == "squelch":
+        return B.Squelch(c["level"]).process(x, c["block"]), None
+    if k == "ssb":
+        blk, off, parts = B.SSBDemod(c["fs"], c["bw"], c["mode"]), 0, []
+        for s in loader.as_blocks(len(x), c["block"]):
+            parts.append(blk.process(x[off:off + s]))
+            off += s
+        return np.concatenate(parts), None
     if k == "costas":
         pl = B.CostasLoop(c["order"], c["bw"])
         pl.set_chunking(c.get("chunk", 0), c.get("warmup", 0))

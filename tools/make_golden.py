@@ -84,6 +84,26 @@ def main():
             gold[name + "_vc"] = vc
         elif k == "costas":
             y = R.costas(c["order"], c["bw"], x, c["block"])
+        elif k == "math":
+            x2 = make_input(c, "src2")
+            y = np.stack([R.math(op, x, x2, c["block"]) for op in range(3)])
+        elif k == "layout":
+            x2 = make_input(c, "src2") if "src2" in c else None
+            y = R.layout(c["op"], x, x2, c["block"])
+            if c["op"] == 3:
+                y = np.stack(y)
+        elif k == "volume":
+            y = R.volume(x, c["volume"], c["call_set"], c["muted"], c["block"])
+        elif k == "threshold":
+            y = R.threshold(x, c["block"])
+        elif k == "delay_imag":
+            y = R.delay_imag(x, c["block"])
+        elif k == "amdemod":
+            y = R.amdemod(x, c["block"])
+        elif k == "squelch":
+            y = R.squelch(c["level"], x, c["block"])
+        elif k == "ssb":
+            y = R.ssbdemod(c["fs"], c["bw"], c["mode"], x, c["block"])
         else:
             raise SystemExit(f"unknown kind {k}")
         gold[name] = np.asarray(y)
