@@ -1,6 +1,7 @@
 // include/dsp/demodulator.h — FloatFMDemod and FMDemod (reference src/dsp/demodulator.h:33-187). The kernel
 // evaluates the reference's fast_arctan2 phase-difference formula with its exact float sequence (not an
-// atan2 of a conjugate product: SURVEY.md Q6). AM/SSB/stereo/MSK/PSK demodulators are outside the hot path.
+// atan2 of a conjugate product: SURVEY.md Q6). Also StereoFMDemod, AMDemod and SSBDemod (:189-497); the MSK/PSK
+// hier-block demodulators are not part of this library yet.
 #pragma once
 #include <dsp/block.h>
 
@@ -125,5 +126,86 @@ namespace dsp {
     public:
         FMDemod() {}
         FMDemod(stream<complex_t>* in, float sampleRate, float deviation) { init(in, sampleRate, deviation); }
+    };
+
+    // AMDemod (reference demodulator.h:332-378): |x| minus its mean over the run() block
+    class AMDemod : public generic_block<AMDemod> {
+    public:
+        AMDemod() {}
+        AMDemod(stream<complex_t>* in) { init(in); }
+        ~AMDemod() {
+            generic_block<AMDemod>::stop();
+            if (h) { qdsp_amdemod_destroy(h); }
+        }
+        void init(stream<complex_t>* in) {
+            _in = in;
+            if (!h) { h = qdsp_amdemod_create(); }
+            generic_block<AMDemod>::registerInput(_in);
+            generic_block<AMDemod>::registerOutput(&out);
+        }
+        void setInput(stream<complex_t>* in) { generic_block<AMDemod>::rebindInput(_in, in); }
+        int run() override {
+            const int count = _in->readDevice(cuStream);
+            if (count < 0) { return -1; }
+            out.acquireWriteDev(cuStream);
+            const int one = count;  // one run() call == one block of the mean (demodulator.h:364-366)
+            const long long n = qdsp_amdemod_process(h, _in->readDev(), out.writeDev(), count, &one, 1, 0, cuStream);
+            _in->flushDevice(cuStream);
+            if (n < 0) { return -1; }
+            if (!out.swapDevice(count, cuStream)) { return -1; }
+            return count;
+        }
+
+        stream<float> out;
+
+    private:
+        stream<complex_t>* _in = nullptr;
+        qdsp_amdemod* h = nullptr;
+    };
+
+    // SSBDemod (reference demodulator.h:380-497): rotate by +-pi*bandWidth/sampleRate per sample, keep the real part
+    class SSBDemod : public generic_block<SSBDemod> {
+    public:
+        SSBDemod() {}
+        SSBDemod(stream<complex_t>* in, float sampleRate, float bandWidth, int mode) { init(in, sampleRate, bandWidth, mode); }
+        ~SSBDemod() {
+            generic_block<SSBDemod>::stop();
+            if (h) { qdsp_ssbdemod_destroy(h); }
+        }
+        enum { MODE_USB, MODE_LSB, MODE_DSB };
+        void init(stream<complex_t>* in, float sampleRate, float bandWidth, int mode) {
+            _in = in;
+            _sampleRate = sampleRate;
+            _bandWidth = bandWidth;
+            _mode = mode;
+            if (h) { qdsp_ssbdemod_destroy(h); }
+            h = qdsp_ssbdemod_create(_sampleRate, _bandWidth, _mode);
+            generic_block<SSBDemod>::registerInput(_in);
+            generic_block<SSBDemod>::registerOutput(&out);
+        }
+        void setInput(stream<complex_t>* in) { generic_block<SSBDemod>::rebindInput(_in, in); }
+        void setSampleRate(float sampleRate) { _sampleRate = sampleRate; reconf(); }
+        void setBandWidth(float bandWidth) { _bandWidth = bandWidth; reconf(); }
+        void setMode(int mode) { _mode = mode; reconf(); }
+        int run() override {
+            const int count = _in->readDevice(cuStream);
+            if (count < 0) { return -1; }
+            out.acquireWriteDev(cuStream);
+            const long long n = qdsp_ssbdemod_process(h, _in->readDev(), out.writeDev(), count, cuStream);
+            _in->flushDevice(cuStream);
+            if (n < 0) { return -1; }
+            if (!out.swapDevice(count, cuStream)) { return -1; }
+            return count;
+        }
+
+        stream<float> out;
+
+    private:
+        // the reference changes phaseDelta without stopping the worker (demodulator.h:425-473); same here
+        void reconf() { qdsp_ssbdemod_configure(h, _sampleRate, _bandWidth, _mode); }
+        int _mode = MODE_USB;
+        float _sampleRate = 1, _bandWidth = 0;
+        stream<complex_t>* _in = nullptr;
+        qdsp_ssbdemod* h = nullptr;
     };
 }

@@ -1,6 +1,6 @@
 // include/dsp/processing.h — FrequencyXlator<T>, AGC, FeedForwardAGC<T>, ComplexAGC (reference
-// src/dsp/processing.h:8-300). The element-wise helpers of that header that are off the hot path (DelayImag,
-// Volume, Squelch, Packer, Threshold) are not part of this library (out of scope).
+// src/dsp/processing.h:8-300) and the element-wise helpers of that header: DelayImag, Volume<T>, Squelch, Threshold
+// (:300-610). Packer<T> (host-side re-blocking) is not part of this library.
 #pragma once
 #include <type_traits>
 #include <dsp/block.h>
@@ -195,5 +195,162 @@ namespace dsp {
         float _setPoint = 1.0f, _maxGain = 65535.0f, _rate = 1e-3f;
         stream<complex_t>* _in = nullptr;
         qdsp_cagc* h = nullptr;
+    };
+
+    // DelayImag (reference processing.h:300-346): out[i] = {in[i].re, in[i-1].im}
+    class DelayImag : public generic_block<DelayImag> {
+    public:
+        DelayImag() {}
+        DelayImag(stream<complex_t>* in) { init(in); }
+        ~DelayImag() {
+            generic_block<DelayImag>::stop();
+            if (h) { qdsp_delayimag_destroy(h); }
+        }
+        void init(stream<complex_t>* in) {
+            _in = in;
+            if (!h) { h = qdsp_delayimag_create(); }
+            generic_block<DelayImag>::registerInput(_in);
+            generic_block<DelayImag>::registerOutput(&out);
+        }
+        void setInput(stream<complex_t>* in) { generic_block<DelayImag>::rebindInput(_in, in); }
+        int run() override {
+            const int count = _in->readDevice(cuStream);
+            if (count < 0) { return -1; }
+            out.acquireWriteDev(cuStream);
+            const long long n = qdsp_delayimag_process(h, _in->readDev(), out.writeDev(), count, cuStream);
+            _in->flushDevice(cuStream);
+            if (n < 0) { return -1; }
+            if (!out.swapDevice(count, cuStream)) { return -1; }
+            return count;
+        }
+
+        stream<complex_t> out;
+
+    private:
+        stream<complex_t>* _in = nullptr;
+        qdsp_delayimag* h = nullptr;
+    };
+
+    // Volume<T> (reference processing.h:348-421), T = float or stereo_t. As in the reference, init() stores the
+    // volume but the applied level stays 1.0 until setVolume() is called (:355-359 vs :371-374).
+    template <class T>
+    class Volume : public generic_block<Volume<T>> {
+        using base = generic_block<Volume<T>>;
+        static_assert(std::is_same<T, float>::value || std::is_same<T, stereo_t>::value, "Volume<float> or Volume<stereo_t>");
+
+    public:
+        Volume() {}
+        Volume(stream<T>* in, float volume) { init(in, volume); }
+        ~Volume() { base::stop(); }
+        void init(stream<T>* in, float volume) {
+            _in = in;
+            _volume = volume;
+            base::registerInput(_in);
+            base::registerOutput(&out);
+        }
+        // (sic) the reference names its setInput "setInputSize" (processing.h:362); both spellings work here
+        void setInputSize(stream<T>* in) { setInput(in); }
+        void setInput(stream<T>* in) { base::rebindInput(_in, in); }
+        void setVolume(float volume) {
+            _volume = volume;
+            level = qdsp_volume_level(_volume);
+        }
+        float getVolume() { return _volume; }
+        void setMuted(bool muted) { _muted = muted; }
+        bool getMuted() { return _muted; }
+        int run() override {
+            const int count = _in->readDevice(base::cuStream);
+            if (count < 0) { return -1; }
+            out.acquireWriteDev(base::cuStream);
+            const long long n = qdsp_volume_process(std::is_same<T, float>::value ? QDSP_F32 : QDSP_CF32, level, _muted ? 1 : 0,
+                                                    _in->readDev(), out.writeDev(), count, base::cuStream);
+            _in->flushDevice(base::cuStream);
+            if (n < 0) { return -1; }
+            if (!out.swapDevice(count, base::cuStream)) { return -1; }
+            return count;
+        }
+
+        stream<T> out;
+
+    private:
+        float level = 1.0f;
+        float _volume = 1.0f;
+        bool _muted = false;
+        stream<T>* _in = nullptr;
+    };
+
+    // Squelch (reference processing.h:424-489): a run() block passes iff 10*log10f(mean |x|) >= level
+    class Squelch : public generic_block<Squelch> {
+    public:
+        Squelch() {}
+        Squelch(stream<complex_t>* in, float level) { init(in, level); }
+        ~Squelch() {
+            generic_block<Squelch>::stop();
+            if (h) { qdsp_squelch_destroy(h); }
+        }
+        void init(stream<complex_t>* in, float level) {
+            _in = in;
+            _level = level;
+            if (!h) { h = qdsp_squelch_create(_level); }
+            qdsp_squelch_set_level(h, _level);
+            generic_block<Squelch>::registerInput(_in);
+            generic_block<Squelch>::registerOutput(&out);
+        }
+        void setInput(stream<complex_t>* in) { generic_block<Squelch>::rebindInput(_in, in); }
+        void setLevel(float level) {
+            _level = level;
+            qdsp_squelch_set_level(h, _level);
+        }
+        float getLevel() { return _level; }
+        int run() override {
+            const int count = _in->readDevice(cuStream);
+            if (count < 0) { return -1; }
+            out.acquireWriteDev(cuStream);
+            const int one = count;  // one run() call == one block of the mean (processing.h:465-468)
+            const long long n = qdsp_squelch_process(h, _in->readDev(), out.writeDev(), count, &one, 1, 0, cuStream);
+            _in->flushDevice(cuStream);
+            if (n < 0) { return -1; }
+            if (!out.swapDevice(count, cuStream)) { return -1; }
+            return count;
+        }
+
+        stream<complex_t> out;
+
+    private:
+        float _level = -50.0f;
+        stream<complex_t>* _in = nullptr;
+        qdsp_squelch* h = nullptr;
+    };
+
+    // Threshold (reference processing.h:554-610): uint8 stream of (x > 0); setLevel/getLevel exist but run() ignores them
+    class Threshold : public generic_block<Threshold> {
+    public:
+        Threshold() {}
+        Threshold(stream<float>* in) { init(in); }
+        ~Threshold() { generic_block<Threshold>::stop(); }
+        void init(stream<float>* in) {
+            _in = in;
+            generic_block<Threshold>::registerInput(_in);
+            generic_block<Threshold>::registerOutput(&out);
+        }
+        void setInput(stream<float>* in) { generic_block<Threshold>::rebindInput(_in, in); }
+        void setLevel(float level) { _level = level; }
+        float getLevel() { return _level; }
+        int run() override {
+            const int count = _in->readDevice(cuStream);
+            if (count < 0) { return -1; }
+            out.acquireWriteDev(cuStream);
+            const long long n = qdsp_threshold_process(_in->readDev(), out.writeDev(), count, cuStream);
+            _in->flushDevice(cuStream);
+            if (n < 0) { return -1; }
+            if (!out.swapDevice(count, cuStream)) { return -1; }
+            return count;
+        }
+
+        stream<uint8_t> out;
+
+    private:
+        float _level = -50.0f;
+        stream<float>* _in = nullptr;
     };
 }

@@ -34,6 +34,9 @@ def test_headers_compile_and_link(qlib, tmp_path):
 #include <dsp/routing.h>
 #include <dsp/sink.h>
 #include <dsp/source.h>
+#include <dsp/math.h>
+#include <dsp/audio.h>
+#include <dsp/convertion.h>
 // the reference's spellings and signatures (SURVEY.md section 8b) must keep compiling
 void wire(dsp::stream<dsp::complex_t>* in, dsp::stream<float>* fin, dsp::stream<dsp::stereo_t>* sin) {
     dsp::filter_window::BlackmanWindow win(300e3f, 75590.55f, 2.4e6f);
@@ -59,6 +62,28 @@ void wire(dsp::stream<dsp::complex_t>* in, dsp::stream<float>* fin, dsp::stream<
     fir.updateWindow(&win); rs.updateWindow(&win); xl.setFrequency(1.0f); vfo.setOffset(2.0f);
     int n = rs.calcOutSize(1000) + rs.getInterpolation() + rs.getDecimation();
     (void)n; (void)sin;
+    // the element-wise rows (math.h, audio.h, convertion.h, processing.h :300-610, demodulator.h :332-497)
+    dsp::Add<dsp::complex_t> add(in, &xl.out);
+    dsp::Substract<float> sub(fin, &fm.out);
+    dsp::Multiply<dsp::complex_t> mul(in, &xl.out);
+    dsp::Add<dsp::stereo_t> adds(sin, &fms.out);
+    dsp::MonoToStereo m2s(fin);
+    dsp::ChannelsToStereo c2s(fin, &fm.out);
+    dsp::StereoToMono s2m(sin);
+    dsp::StereoToChannels s2c(sin);
+    dsp::ComplexToStereo cts(in);
+    dsp::ComplexToReal ctr(in);
+    dsp::ComplexToImag cti(in);
+    dsp::RealToComplex rtc(fin);
+    dsp::DelayImag di(in);
+    dsp::Volume<float> vol(fin, 0.5f);
+    dsp::Volume<dsp::stereo_t> vols(sin, 0.5f);
+    dsp::Squelch sq(in, -50.0f);
+    dsp::Threshold th(fin);
+    dsp::AMDemod am(in);
+    dsp::SSBDemod ssb(in, 48e3f, 3e3f, dsp::SSBDemod::MODE_USB);
+    vol.setVolume(0.7f); vol.setMuted(false); vols.setInputSize(sin); sq.setLevel(-40.0f); ssb.setMode(dsp::SSBDemod::MODE_LSB);
+    ssb.setBandWidth(2.8e3f); c2s.setInput(fin, &fm.out); (void)s2c.out_left.writeBuf; (void)th.out.readBuf;
     fir.start(); fir.stop();
 }
 int main() { return qdsp_abi_version() == 1 ? 0 : 1; }
@@ -70,6 +95,38 @@ int main() { return qdsp_abi_version() == 1 ? 0 : 1; }
     assert subprocess.call([str(exe)]) == 0
     _build(qlib)
     assert os.path.exists(EXE)
+
+
+@pytest.mark.gpu
+def test_cpp_am_graph_matches_oracle(qlib, tmp_path):
+    # Squelch -> AMDemod -> Volume -> MonoToStereo -> StereoToMono through the thread-per-block plumbing
+    from oracle import loader
+    from tests.cases import CASES, make_input
+
+    exe = tmp_path / "am_chain"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "am_chain.cpp"),
+                           "-L" + os.path.join(ROOT, "qdsp_b200"), "-lqdsp_b200", "-lpthread",
+                           "-Wl,-rpath," + os.path.join(ROOT, "qdsp_b200"), "-o", str(exe)])
+    x = make_input(CASES["squelch"])            # three blocks: pass, mute, pass
+    blocks = CASES["squelch"]["block"]
+    fin, fout = tmp_path / "in.cf32", tmp_path / "out.f32"
+    P = loader.port()
+    want = []
+    off = 0
+    for s in blocks:                            # the C++ feeder reads fixed-size blocks: run one process per block size
+        seg = x[off:off + s]
+        y = P.squelch(-30.0, seg, [s])
+        y = P.amdemod(y, [s])
+        y = P.volume(y, 0.5, 1, 0)
+        y = P.layout(2, P.layout(0, y))
+        want.append(y)
+        seg.tofile(fin)
+        subprocess.check_call([str(exe), str(fin), str(fout), str(s)], timeout=120)
+        got = np.fromfile(fout, np.float32)
+        assert got.shape == y.shape
+        assert np.abs(got - y).max() <= 1e-5
+        off += s
+    assert not np.any(want[1]) and np.any(want[0]) and np.any(want[2])
 
 
 @pytest.mark.gpu

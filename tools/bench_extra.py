@@ -1,4 +1,5 @@
-"""tools/bench_extra.py — device-resident throughput of the non-headline BASELINE configs (1a, 1b, 3, 4, 5).
+"""tools/bench_extra.py — device-resident throughput of the non-headline BASELINE configs (1a, 1b, 3, 4, 5) and of the
+element-wise "next" rows (pw).
 One JSON line per config. Inputs are generated on the device; timing = CUDA events over `steps` passes.
     python tools/bench_extra.py [--configs 1a,1b,3,4,5] [--steps 5]"""
 import argparse
@@ -33,7 +34,7 @@ def timed(fn, steps, warmup=2):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="1a,1b,3,4,5")
+    ap.add_argument("--configs", default="1a,1b,3,4,5,pw")
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--n3", type=int, default=1 << 26, help="samples for config 3 (full config: 2^30)")
     ap.add_argument("--n4", type=int, default=1 << 24, help="wideband samples for config 4 (full: 2^26)")
@@ -109,6 +110,30 @@ def main():
         ms = timed(lambda: agc.process_device(xf.data_ptr(), yf.data_ptr(), 2 * n, 1000000, stream=sp), args.steps, warmup=1)
         print(json.dumps({"config": f"5 AGC, {2 * n} floats, run() blocks of 1e6", "ms": ms, "Msamples_s": 2 * n / ms / 1e3,
                           "hbm_gbs": 8 * 2 * n / ms / 1e6, "frac_hbm_measured": 8 * 2 * n / ms / 1e6 / hbm}), flush=True)
+    if "pw" in cfgs:
+        # element-wise / layout / per-block-statistic rows: all HBM-bound, algorithmic bytes per sample in the table
+        n = 1 << 26
+        x = uniform(n, 6)
+        x2 = uniform(n, 7)
+        y = torch.empty(n, dtype=torch.complex64, device="cuda")
+        Lc = lib.load()
+        xp, x2p, yp = x.data_ptr(), x2.data_ptr(), y.data_ptr()
+        am, sq, ssb, di = B.AMDemod(), B.Squelch(-30.0), B.SSBDemod(48e3, 3e3, 0), B.DelayImag()
+        rows = [
+            ("Add<complex_t>", 24, lambda: Lc.qdsp_math_process(0, 1, xp, x2p, yp, n, sp)),
+            ("Multiply<complex_t>", 24, lambda: Lc.qdsp_math_process(2, 1, xp, x2p, yp, n, sp)),
+            ("StereoToMono", 12, lambda: Lc.qdsp_layout_process(2, xp, None, yp, None, n, sp)),
+            ("StereoToChannels", 16, lambda: Lc.qdsp_layout_process(3, xp, None, yp, yp + 4 * n, n, sp)),
+            ("Volume<stereo_t>", 16, lambda: Lc.qdsp_volume_process(1, 0.49, 0, xp, yp, n, sp)),
+            ("DelayImag", 16, lambda: di.process_device(xp, yp, n, stream=sp)),
+            ("AMDemod, run() blocks of 1e6 (12 B algorithmic, 20 B moved)", 12, lambda: am.process_device(xp, yp, n, 1000000, stream=sp)),
+            ("Squelch, run() blocks of 1e6 (16 B algorithmic, 24 B moved)", 16, lambda: sq.process_device(xp, yp, n, 1000000, stream=sp)),
+            ("SSBDemod", 12, lambda: ssb.process_device(xp, yp, n, stream=sp)),
+        ]
+        for name, bytes_per, fn in rows:
+            ms = timed(fn, args.steps, warmup=1)
+            print(json.dumps({"config": f"pw {name}, {n} elements", "ms": ms, "Msamples_s": n / ms / 1e3,
+                              "hbm_gbs": bytes_per * n / ms / 1e6, "frac_hbm_measured": bytes_per * n / ms / 1e6 / hbm}), flush=True)
 
 
 if __name__ == "__main__":
