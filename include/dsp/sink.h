@@ -2,6 +2,8 @@
 // graph. read() on a device-produced stream performs the single D2H copy; the handler then sees `readBuf` as
 // ordinary (pinned) host memory, exactly like in the reference.
 #pragma once
+#include <fstream>
+#include <string>
 #include <dsp/block.h>
 
 namespace dsp {
@@ -62,5 +64,37 @@ namespace dsp {
 
     private:
         stream<T>* _in = nullptr;
+    };
+
+    // FileSink<T> (reference sink.h:135-178): `read()` downloads a device-produced block into the pinned `readBuf`
+    template <class T>
+    class FileSink : public generic_block<FileSink<T>> {
+        using base = generic_block<FileSink<T>>;
+
+    public:
+        FileSink() {}
+        FileSink(stream<T>* in, std::string path) { init(in, path); }
+        ~FileSink() {
+            base::stop();
+            if (file.is_open()) { file.close(); }
+        }
+        void init(stream<T>* in, std::string path) {
+            _in = in;
+            file = std::ofstream(path, std::ios::binary);
+            base::registerInput(_in);
+        }
+        void setInput(stream<T>* in) { base::rebindInput(_in, in); }
+        bool isOpen() { return file.is_open(); }
+        int run() override {
+            const int count = _in->read();
+            if (count < 0) { return -1; }
+            if (file.is_open()) { file.write((char*)_in->readBuf, (std::streamsize)count * sizeof(T)); }
+            _in->flush();
+            return count;
+        }
+
+    private:
+        stream<T>* _in = nullptr;
+        std::ofstream file;
     };
 }

@@ -292,6 +292,16 @@ void qdsp_ssbdemod_get_phase(qdsp_ssbdemod* h, float* re, float* im);
 void qdsp_ssbdemod_set_phase(qdsp_ssbdemod* h, float re, float im);
 long long qdsp_ssbdemod_process(qdsp_ssbdemod* h, const void* in_dev, float* out_dev, long long count, qdsp_stream_t s);
 
+/* SineSource::run, src/dsp/source.h:55-59: the VOLK rotator over a buffer of ones, i.e. the NCO phasor itself
+ * (closed form here); one call produces one block of `count` samples */
+typedef struct qdsp_sinesource qdsp_sinesource;
+qdsp_sinesource* qdsp_sinesource_create(float sampleRate, float freq);
+void qdsp_sinesource_destroy(qdsp_sinesource* h);
+int qdsp_sinesource_configure(qdsp_sinesource* h, float sampleRate, float freq);   /* setSampleRate / setFrequency */
+void qdsp_sinesource_get_phase(qdsp_sinesource* h, float* re, float* im);
+void qdsp_sinesource_set_phase(qdsp_sinesource* h, float re, float im);
+long long qdsp_sinesource_process(qdsp_sinesource* h, void* out_dev, long long count, qdsp_stream_t s);
+
 /* ---- device-side synthetic IQ (bench inputs; same integer recipe as qdsp_b200/synth.py) ------ */
 int qdsp_synth_uniform_cf32(void* out_dev, unsigned long long seed, long long start, long long count, qdsp_stream_t s);
 int qdsp_synth_fm_cf32(void* out_dev, long long start, long long count, long long fs, long long fc, long long fm,

@@ -963,3 +963,51 @@ class SSBDemod(_Block):
 
     def _run(self, in_ptr, out_ptr, n, block):
         return _L().qdsp_ssbdemod_process(self.h, in_ptr, out_ptr, n, self.stream)
+
+
+class SineSource:
+    """dsp::SineSource: init(blockSize, sampleRate, freq) (source.h:5-71); generate() is one run() call."""
+
+    def __init__(self, blockSize: int, sampleRate: float, freq: float):
+        _lib.require_device()
+        self._blockSize, self._sampleRate, self._freq = int(blockSize), float(sampleRate), float(freq)
+        self.h = check(_L().qdsp_sinesource_create(self._sampleRate, self._freq), "qdsp_sinesource_create")
+
+    def setBlockSize(self, n):  # noqa: N802
+        self._blockSize = int(n)
+
+    def getBlockSize(self):  # noqa: N802
+        return self._blockSize
+
+    def setSampleRate(self, v):  # noqa: N802
+        self._sampleRate = float(v)
+        _L().qdsp_sinesource_configure(self.h, self._sampleRate, self._freq)
+
+    def setFrequency(self, v):  # noqa: N802
+        self._freq = float(v)
+        _L().qdsp_sinesource_configure(self.h, self._sampleRate, self._freq)
+
+    def getFrequency(self):  # noqa: N802
+        return self._freq
+
+    def generate_device(self, out_ptr, stream=None) -> int:
+        return int(check(_L().qdsp_sinesource_process(self.h, out_ptr, self._blockSize, stream), "SineSource"))
+
+    def generate(self) -> np.ndarray:
+        d = DevBuf(max(self._blockSize * 8, 16))
+        m = self.generate_device(d.ptr)
+        y = d.to_numpy(np.complex64, m)
+        d.free()
+        return y
+
+    def close(self):
+        if self.h:
+            _L().qdsp_sinesource_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+

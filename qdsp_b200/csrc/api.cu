@@ -1004,6 +1004,15 @@ struct qdsp_squelch {
     Partition part;
     Scratch scratch;
 };
+struct qdsp_sinesource {
+    Nco nco;
+    float2 inc_pow[3];
+    void configure(float sampleRate, float freq) {
+        nco.set_freq(sampleRate, freq);   // source.h:20 is the translator's expression (processing.h:21)
+        const double th = atan2((double)nco.inc_im, (double)nco.inc_re);
+        for (int j = 1; j <= 3; j++) inc_pow[j - 1] = make_float2((float)cos(th * j), (float)sin(th * j));
+    }
+};
 struct qdsp_ssbdemod {
     Nco nco;
     float2 inc_pow[3];
@@ -1165,6 +1174,29 @@ long long qdsp_ssbdemod_process(qdsp_ssbdemod* h, const void* in_dev, float* out
     if (count < 0) return -1;
     if (launch_ssb((const float2*)in_dev, out_dev, count, h->nco.phase, h->nco.step, h->inc_pow[0], h->inc_pow[1],
                    h->inc_pow[2], as_stream(s)) != 0)
+        return -1;
+    h->nco.advance(count);
+    return count;
+}
+
+qdsp_sinesource* qdsp_sinesource_create(float sampleRate, float freq) {
+    qdsp_sinesource* h = new (std::nothrow) qdsp_sinesource();
+    if (!h) return nullptr;
+    h->configure(sampleRate, freq);
+    h->nco.phase = 0;   // phase = (1, 0), source.h:19
+    return h;
+}
+void qdsp_sinesource_destroy(qdsp_sinesource* h) { delete h; }
+int qdsp_sinesource_configure(qdsp_sinesource* h, float sampleRate, float freq) {
+    h->configure(sampleRate, freq);
+    return 0;
+}
+void qdsp_sinesource_get_phase(qdsp_sinesource* h, float* re, float* im) { h->nco.get_phase(re, im); }
+void qdsp_sinesource_set_phase(qdsp_sinesource* h, float re, float im) { h->nco.set_phase(re, im); }
+long long qdsp_sinesource_process(qdsp_sinesource* h, void* out_dev, long long count, qdsp_stream_t s) {
+    if (count < 0) return -1;
+    if (launch_sine((float2*)out_dev, count, h->nco.phase, h->nco.step, h->inc_pow[0], h->inc_pow[1], h->inc_pow[2],
+                    as_stream(s)) != 0)
         return -1;
     h->nco.advance(count);
     return count;

@@ -13,6 +13,7 @@
 //     9*16 B, which is conflict-free for 128-bit shared loads.
 //   * the whole input window of a tile stays resident (NOUT + T - 1 samples), so the tap loop runs
 //     without any block-level barrier; two CTAs per SM overlap one tile's staging with the other's math.
+#include <stdlib.h>
 #include <new>
 #include <vector>
 #include "internal.cuh"
@@ -153,12 +154,12 @@ fir_dense_kernel(VStream<float2> xs, long long count, const float2* __restrict__
 struct FirDecimPlan {
     int T = 0, D = 0;
     int U = 0;                   // tap pairs per (sub-stream, parity) table, multiple of kFirR
-    float2* taps_dev = nullptr;  // [D][2][U]
+    float2* taps_dev = nullptr;  // [2 pads][D][2][U]
 };
 
 FirDecimPlan* fir_decim_plan_create(const float* taps, int T, int D) {
     if (T < 2 || D < 2 || D > 8) return nullptr;
-    const int tq = (T + D - 1) / D;              // taps of the longest sub-filter
+    const int tq = (T + 1 + D - 1) / D;          // taps of the longest sub-filter (one more tap slot for pad = 1)
     int U = (tq + 2) / 2;
     U = ((U + kFirR - 1) / kFirR) * kFirR;
     const size_t smem = (size_t)D * (kFirNout / 2 + U + 8) * 16 + (size_t)D * 2 * U * 8;
@@ -168,17 +169,20 @@ FirDecimPlan* fir_decim_plan_create(const float* taps, int T, int D) {
     p->T = T;
     p->D = D;
     p->U = U;
-    std::vector<float2> tab((size_t)D * 2 * U, make_float2(0.f, 0.f));
-    for (int r = 0; r < D; r++) {
-        auto h = [&](int q) {
-            const int t = D * q + r;
-            return (q >= 0 && t < T) ? taps[t] : 0.0f;
-        };
-        for (int u = 0; u < U; u++) {
-            tab[((size_t)r * 2 + 0) * U + u] = make_float2(h(2 * u), h(2 * u + 1));
-            tab[((size_t)r * 2 + 1) * U + u] = make_float2(h(2 * u - 1), h(2 * u));
+    // [pad][D][2][U]: the tile's first staged sample is moved back by pad = 0 / 1 so that it sits on an even sample
+    // index (128-bit global loads); the taps move with it: g[t] = h[t - pad]
+    std::vector<float2> tab((size_t)2 * D * 2 * U, make_float2(0.f, 0.f));
+    for (int pad = 0; pad < 2; pad++)
+        for (int r = 0; r < D; r++) {
+            auto h = [&](int q) {
+                const int t = D * q + r - pad;
+                return (q >= 0 && t >= 0 && t < T) ? taps[t] : 0.0f;
+            };
+            for (int u = 0; u < U; u++) {
+                tab[(((size_t)pad * D + r) * 2 + 0) * U + u] = make_float2(h(2 * u), h(2 * u + 1));
+                tab[(((size_t)pad * D + r) * 2 + 1) * U + u] = make_float2(h(2 * u - 1), h(2 * u));
+            }
         }
-    }
     if (cudaMalloc(&p->taps_dev, tab.size() * sizeof(float2)) != cudaSuccess ||
         cudaMemcpy(p->taps_dev, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) {
         set_last_error("fir_decim_plan_create: tap upload failed");
@@ -193,20 +197,51 @@ void fir_decim_plan_destroy(FirDecimPlan* p) {
     delete p;
 }
 
+// DT > 0: compile-time decimation with vectorised staging (one thread moves 2*D consecutive samples = D 128-bit
+// global loads into D sample quads = D 128-bit shared stores); DT == 0: run-time D, scalar staging.
+template <int DT>
 __global__ void __launch_bounds__(kFirThreads, 2)
-fir_decim_kernel(VStream<float2> xs, long long count, long long n_out, const float2* __restrict__ taps, int T, int D,
+fir_decim_kernel(VStream<float2> xs, long long count, long long n_out, const float2* __restrict__ taps, int T, int Drt,
                  int U, float2* __restrict__ out) {
     constexpr int R = kFirR;
+    const int D = DT ? DT : Drt;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int npairs = kFirNout / 2 + U + 8;                         // per sub-stream
     float4* sq = reinterpret_cast<float4*>(smem_raw);                 // [D][npairs] sample quads
     float2* st = reinterpret_cast<float2*>(smem_raw + (size_t)D * npairs * 16);  // [D][2][U]
     const int t = threadIdx.x;
     const long long k_t = (long long)blockIdx.x * kFirNout;           // first output of the tile
-    const long long B = (long long)D * k_t - T;                       // sample index of sub-stream 0, element 0
+    // with DT the staged window starts on an even sample index (pad = 0 / 1 samples earlier; the tap tables of that pad
+    // are shifted by the same amount)
+    const int pad = DT ? (int)(((long long)D * k_t - T) & 1) : 0;
+    const long long B = (long long)D * k_t - T - pad;                 // sample index of sub-stream 0, element 0
 
-    for (int i = t; i < D * 2 * U; i += kFirThreads) st[i] = taps[i];
     {
+        const float2* tsrc = taps + (size_t)pad * D * 2 * U;
+        for (int i = t; i < D * 2 * U; i += kFirThreads) st[i] = tsrc[i];
+    }
+    if (DT) {
+        const bool in_aligned = (reinterpret_cast<uintptr_t>(xs.in) & 15) == 0;
+        for (int g = t; g < npairs; g += kFirThreads) {
+            const long long i0 = B + (long long)2 * DT * g;          // even
+            float2 v[2 * (DT ? DT : 1)];
+            if (in_aligned && i0 >= 0 && i0 + 2 * DT <= count) {
+                const float4* src = reinterpret_cast<const float4*>(xs.in + i0);
+#pragma unroll
+                for (int j = 0; j < DT; j++) {
+                    const float4 a = ldg_stream128(src + j);
+                    v[2 * j] = make_float2(a.x, a.y);
+                    v[2 * j + 1] = make_float2(a.z, a.w);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 2 * DT; j++) v[j] = (i0 + j < count) ? xs.at(i0 + j) : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int r = 0; r < DT; r++)   // sub-stream r: elements 2g and 2g+1 are the unit's samples r and D + r
+                sq[(size_t)r * npairs + g] = make_float4(v[r].x, v[DT + r].x, v[r].y, v[DT + r].y);
+        }
+    } else {
         float* sf = reinterpret_cast<float*>(sq);
         const int nsamp = 2 * npairs * D;                             // consecutive input samples of the tile
         for (int e0 = t; e0 < nsamp; e0 += 8 * kFirThreads) {
@@ -275,14 +310,19 @@ int launch_fir_decim(FirDecimPlan* plan, const float2* hist, int H, const float2
     if (n_out <= 0) return 0;
     VStream<float2> xs{hist, in, H};
     const size_t smem = (size_t)plan->D * (kFirNout / 2 + plan->U + 8) * 16 + (size_t)plan->D * 2 * plan->U * 8;
-    static bool attr_set = false;
-    if (!attr_set) {
-        QDSP_CUDA_OK(cudaFuncSetAttribute(fir_decim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-        attr_set = true;
-    }
     const long long tiles = (n_out + kFirNout - 1) / kFirNout;
-    fir_decim_kernel<<<(unsigned)tiles, kFirThreads, smem, s>>>(xs, count, n_out, plan->taps_dev, plan->T, plan->D,
-                                                                plan->U, out);
+#define QDSP_FIR_DECIM_LAUNCH(DT)                                                                                  \
+    {                                                                                                              \
+        QDSP_CUDA_OK(cudaFuncSetAttribute(fir_decim_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); \
+        fir_decim_kernel<DT><<<(unsigned)tiles, kFirThreads, smem, s>>>(xs, count, n_out, plan->taps_dev, plan->T, plan->D, \
+                                                                        plan->U, out);                             \
+    }
+    static const bool scalar_staging = getenv("QDSP_FIR_DECIM_SCALAR") != nullptr;   // A/B switch
+    if (!scalar_staging && plan->D == 2) QDSP_FIR_DECIM_LAUNCH(2)
+    else if (!scalar_staging && plan->D == 4) QDSP_FIR_DECIM_LAUNCH(4)
+    else if (!scalar_staging && plan->D == 8) QDSP_FIR_DECIM_LAUNCH(8)
+    else QDSP_FIR_DECIM_LAUNCH(0)
+#undef QDSP_FIR_DECIM_LAUNCH
     QDSP_LAUNCH_OK();
     return 0;
 }

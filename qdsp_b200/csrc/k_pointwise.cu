@@ -316,4 +316,26 @@ int launch_ssb(const float2* in, float* out, long long count, uint64_t phase0, u
     return 0;
 }
 
+// ---- SineSource::run (source.h:56): VOLK rotator over a buffer of ones == the NCO phasor itself -----------
+__global__ void __launch_bounds__(256) sine_kernel(float2* __restrict__ out, long long count, uint64_t phase0, uint64_t step,
+                                                   float2 inc1, float2 inc2, float2 inc3) {
+    const long long nquad = (count + 3) >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < nquad; q += stride) {
+        const long long n = q << 2;
+        const float2 p0 = phasor_from_turns(phase0 + step * (uint64_t)n);
+        const float2 p[4] = {p0, cmul(p0, inc1), cmul(p0, inc2), cmul(p0, inc3)};
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (n + j < count) out[n + j] = p[j];
+    }
+}
+int launch_sine(float2* out, long long count, uint64_t phase0, uint64_t step, float2 inc1, float2 inc2, float2 inc3,
+                cudaStream_t s) {
+    if (count <= 0) return 0;
+    sine_kernel<<<pw_grid(count / 4 + 1, 256, 8), 256, 0, s>>>(out, count, phase0, step, inc1, inc2, inc3);
+    QDSP_LAUNCH_OK();
+    return 0;
+}
+
 }  // namespace qdsp

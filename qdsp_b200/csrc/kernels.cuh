@@ -82,6 +82,8 @@ int launch_delay_imag(const float2* in, float2* out, long long count, const floa
 size_t mag_scratch_bytes(int nblocks);
 int launch_amdemod(const float2* in, float* out, const Partition& part, double* partial, cudaStream_t s);
 int launch_squelch(const float2* in, float2* out, const Partition& part, double* partial, float level, cudaStream_t s);
+int launch_sine(float2* out, long long count, uint64_t phase0, uint64_t step, float2 inc1, float2 inc2, float2 inc3,
+                cudaStream_t s);
 int launch_ssb(const float2* in, float* out, long long count, uint64_t phase0, uint64_t step, float2 inc1, float2 inc2,
                float2 inc3, cudaStream_t s);
 

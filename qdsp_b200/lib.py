@@ -165,6 +165,12 @@ SIGNATURES = {
     "qdsp_ssbdemod_get_phase": (None, [_vp, _fp, _fp]),
     "qdsp_ssbdemod_set_phase": (None, [_vp, _f, _f]),
     "qdsp_ssbdemod_process": (_ll, [_vp, _vp, _vp, _ll, _vp]),
+    "qdsp_sinesource_create": (_vp, [_f, _f]),
+    "qdsp_sinesource_destroy": (None, [_vp]),
+    "qdsp_sinesource_configure": (_i, [_vp, _f, _f]),
+    "qdsp_sinesource_get_phase": (None, [_vp, _fp, _fp]),
+    "qdsp_sinesource_set_phase": (None, [_vp, _f, _f]),
+    "qdsp_sinesource_process": (_ll, [_vp, _vp, _ll, _vp]),
     "qdsp_synth_uniform_cf32": (_i, [_vp, _ull, _ll, _ll, _vp]),
     "qdsp_synth_fm_cf32": (_i, [_vp, _ll, _ll, _ll, _ll, _ll, _d, _d, _d, _ull, _vp]),
     "qdsp_measure_fp32_peak": (_d, [_i, _i]),

@@ -84,6 +84,8 @@ void wire(dsp::stream<dsp::complex_t>* in, dsp::stream<float>* fin, dsp::stream<
     dsp::SSBDemod ssb(in, 48e3f, 3e3f, dsp::SSBDemod::MODE_USB);
     vol.setVolume(0.7f); vol.setMuted(false); vols.setInputSize(sin); sq.setLevel(-40.0f); ssb.setMode(dsp::SSBDemod::MODE_LSB);
     ssb.setBandWidth(2.8e3f); c2s.setInput(fin, &fm.out); (void)s2c.out_left.writeBuf; (void)th.out.readBuf;
+    dsp::SineSource sine(1000, 48e3f, 1e3f); sine.setFrequency(2e3f); (void)sine.getBlockSize();
+    dsp::FileSink<float> fs(&fm.out, "/dev/null"); (void)fs.isOpen();
     fir.start(); fir.stop();
 }
 int main() { return qdsp_abi_version() == 1 ? 0 : 1; }

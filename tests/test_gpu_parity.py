@@ -480,3 +480,41 @@ def test_layout_round_trips_large():
     assert np.array_equal(B.Threshold().process(l), (l > 0).astype(np.uint8))
     prod = B.Multiply().process(x, np.conj(x))
     assert np.max(np.abs(prod.imag)) <= 1e-6 and np.allclose(prod.real, np.abs(x) ** 2, rtol=1e-6)
+
+
+def test_sine_source():
+    # SineSource::run is the VOLK rotator over ones (source.h:56): parity vs the recursive float phasor for a short
+    # stream, vs the drift-free float64 rotator for a long one; the phase carries across run() calls
+    from qdsp_b200 import blocks as B
+
+    P = loader.port()
+    src = B.SineSource(4000, 48e3, 1234.5)
+    y = np.concatenate([src.generate(), src.generate(), src.generate()])
+    inc = P.xlator_phase_delta(48e3, 1234.5)
+    ones = np.ones(len(y), np.complex64)
+    ref, _ = P.rotator(ones, inc, 1 + 0j, 4000)
+    assert rel_l2(y, ref) <= IQ_TOL
+    y64, _ = P.rotator_f64(ones, inc)
+    assert rel_l2(y, y64) <= 1e-6
+    assert np.max(np.abs(np.abs(y) - 1.0)) <= 2e-7
+
+
+@pytest.mark.parametrize("decim,ntaps_fs", [(2, 2.4e6), (8, 2.4e6), (4, 2.4e6)])
+def test_small_decimation_fir_kernel_variants(decim, ntaps_fs):
+    # fir_decim_kernel<2|4|8> (vectorised staging, pad-shifted tap tables) against the C restatement, with history
+    # carried across two calls and a block grid that makes the tile base odd and even
+    from qdsp_b200 import blocks as B, synth
+
+    P = loader.port()
+    n = 3 * 18432 + 8 * 33
+    x = synth.uniform_cf32(77, 0, n)
+    for win in ((300e3, 4 * ntaps_fs / 127, ntaps_fs), (200e3, 4 * ntaps_fs / 64, ntaps_fs)):   # odd and even tap counts
+        taps = P.blackman_taps(*win)
+        r = B.PolyphaseResampler(B.BlackmanWindow(*win), ntaps_fs, ntaps_fs / decim)
+        assert (r.getInterpolation(), r.getDecimation()) == (1, decim)
+        blk = 8 * 1153
+        y = np.concatenate([r.process(x[:5 * blk], blk), r.process(x[5 * blk:], blk)])
+        sizes = list(loader.as_blocks(5 * blk, blk)) + list(loader.as_blocks(n - 5 * blk, blk))
+        yo, _ = P.resamp_cf32(taps, 1, decim, x, sizes)
+        assert y.shape == yo.shape
+        assert rel_l2(y, yo) <= IQ_TOL, (decim, len(taps), rel_l2(y, yo))
