@@ -66,6 +66,22 @@ void fir_plan_destroy(FirPlan* p) {
     delete p;
 }
 
+// a tile of kFirNout outputs parked in shared memory -> global, 128-bit stores when the destination allows
+__device__ __forceinline__ void store_tile(const float2* so, float2* __restrict__ out, long long first, long long limit) {
+    const int t = threadIdx.x;
+    const long long left = limit - first;
+    const int nvalid = left < kFirNout ? (int)left : kFirNout;
+    float2* dst = out + first;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        const int nq = nvalid >> 1;
+        for (int q = t; q < nq; q += kFirThreads)
+            reinterpret_cast<float4*>(dst)[q] = reinterpret_cast<const float4*>(so)[q];
+        if (t == 0 && (nvalid & 1)) dst[nvalid - 1] = so[nvalid - 1];
+    } else {
+        for (int i = t; i < nvalid; i += kFirThreads) dst[i] = so[i];
+    }
+}
+
 __global__ void __launch_bounds__(kFirThreads, 2)
 fir_dense_kernel(VStream<float2> xs, long long count, const float2* __restrict__ taps, int T, int U,
                  float2* __restrict__ out) {
@@ -80,7 +96,29 @@ fir_dense_kernel(VStream<float2> xs, long long count, const float2* __restrict__
 
     // ---- staging: taps, then the tile's window as (re, re, im, im) quads --------------------------
     for (int i = t; i < 2 * U; i += kFirThreads) st[i] = taps[i];
-    {
+    if ((B & 1) == 0 && (reinterpret_cast<uintptr_t>(xs.in) & 15) == 0) {
+        // the window starts on an even sample (odd tap counts): one 128-bit load -> one quad, 4 in flight per thread
+        for (int q0 = t; q0 < npairs; q0 += 4 * kFirThreads) {
+            float4 a[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int q = q0 + j * kFirThreads;
+                const long long i0 = B + 2 * (long long)q;
+                if (q < npairs && i0 >= 0 && i0 + 2 <= count) {
+                    a[j] = ldg_stream128(reinterpret_cast<const float4*>(xs.in + i0));
+                } else {
+                    const float2 v0 = (q < npairs && i0 < count) ? xs.at(i0) : make_float2(0.f, 0.f);
+                    const float2 v1 = (q < npairs && i0 + 1 < count) ? xs.at(i0 + 1) : make_float2(0.f, 0.f);
+                    a[j] = make_float4(v0.x, v0.y, v1.x, v1.y);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int q = q0 + j * kFirThreads;
+                if (q < npairs) sq[q] = make_float4(a[j].x, a[j].z, a[j].y, a[j].w);
+            }
+        }
+    } else {
         float* sf = reinterpret_cast<float*>(sq);
         const int nsamp = 2 * npairs;
         // batches of 8 loads per thread in flight together (a one-at-a-time loop exposes the DRAM latency 8x)
@@ -135,12 +173,15 @@ fir_dense_kernel(VStream<float2> xs, long long count, const float2* __restrict__
             W[k] = win[u0 + k + R];               // S_{j0 + (u0+k+1) + (R-1)} replaces S_{j0 + u0 + k}
         }
     }
-    // ---- store: outputs n = n_t + 2*(j0 + i) + parity ------------------------------------------------
+    // ---- store: outputs n = n_t + 2*(j0 + i) + parity. A thread's outputs are 16 bytes apart and the lanes 144:
+    // exchange them through the (now dead) sample window so that the tile leaves as coalesced 128-bit stores ----
+    __syncthreads();
+    float2* so = reinterpret_cast<float2*>(smem_raw);                 // [kFirNout], 18 KB <= the window's footprint
 #pragma unroll
-    for (int i = 0; i < R; i++) {
-        const long long n = n_t + 2 * (long long)(j0 + i) + parity;
-        if (n < count) out[n] = make_float2(accRe[i].x + accRe[i].y, accIm[i].x + accIm[i].y);
-    }
+    for (int i = 0; i < R; i++)
+        so[2 * (j0 + i) + parity] = make_float2(accRe[i].x + accRe[i].y, accIm[i].x + accIm[i].y);
+    __syncthreads();
+    store_tile(so, out, n_t, count);
 }
 
 // =================================================================================================
@@ -297,11 +338,13 @@ fir_decim_kernel(VStream<float2> xs, long long count, long long n_out, const flo
             }
         }
     }
+    __syncthreads();
+    float2* so = reinterpret_cast<float2*>(smem_raw);                 // [kFirNout] outputs, then coalesced stores
 #pragma unroll
-    for (int i = 0; i < R; i++) {
-        const long long k = k_t + 2 * (long long)(j0 + i) + parity;
-        if (k < n_out) out[k] = make_float2(accRe[i].x + accRe[i].y, accIm[i].x + accIm[i].y);
-    }
+    for (int i = 0; i < R; i++)
+        so[2 * (j0 + i) + parity] = make_float2(accRe[i].x + accRe[i].y, accIm[i].x + accIm[i].y);
+    __syncthreads();
+    store_tile(so, out, k_t, n_out);
 }
 
 // count input samples (one regular partition: every run() block a multiple of D, so the output grid is uniform)
