@@ -51,7 +51,9 @@ namespace dsp {
     private:
         void loadTaps(dsp::filter_window::generic_window* window) {
             const int tapCount = window->getTapCount();
-            std::vector<float> taps(tapCount);
+            // RRCTaps::createTaps rounds an even count up and writes tapCount | 1 taps (window.h:186): the reference
+            // overflows its buffer by one float there and filters with the first tapCount of them; same taps, no overflow
+            std::vector<float> taps((size_t)tapCount | 1);
             window->createTaps(taps.data(), tapCount);
             if (!h) { h = qdsp_fir_create(std::is_same<T, float>::value ? QDSP_F32 : QDSP_CF32, taps.data(), tapCount); }
             else { qdsp_fir_set_taps(h, taps.data(), tapCount); }

@@ -78,7 +78,9 @@ namespace dsp {
     private:
         void rebuild() {
             const int tapCount = _window->getTapCount();
-            std::vector<float> taps(tapCount);
+            // RRCTaps::createTaps rounds an even count up and writes tapCount | 1 taps (window.h:186): the reference
+            // overflows its buffer by one float there and filters with the first tapCount of them; same taps, no overflow
+            std::vector<float> taps((size_t)tapCount | 1);
             _window->createTaps(taps.data(), tapCount, (float)_interp);
             if (h) { qdsp_resamp_destroy(h); }
             h = qdsp_resamp_create(std::is_same<T, float>::value ? QDSP_F32 : QDSP_CF32, taps.data(), tapCount, _interp, _decim);

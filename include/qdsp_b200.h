@@ -292,6 +292,26 @@ void qdsp_ssbdemod_get_phase(qdsp_ssbdemod* h, float* re, float* im);
 void qdsp_ssbdemod_set_phase(qdsp_ssbdemod* h, float re, float im);
 long long qdsp_ssbdemod_process(qdsp_ssbdemod* h, const void* in_dev, float* out_dev, long long count, qdsp_stream_t s);
 
+/* ---- MMClockRecovery<float | complex_t>::run, src/dsp/clock_recovery.h:127-215 ("next" row) ------------------ *
+ * Symbol-timing recovery: out_dev receives the recovered symbols (at most qdsp_mm_max_out(count) of them), the     *
+ * return value is their number (data dependent, so this call waits for the kernel; out_counts, optional, gets the *
+ * per-run()-block counts the reference passes to out.swap()). `interp_taps` is the caller's INTERP_TAPS[129][8]    *
+ * (src/dsp/interpolation_taps.h:6-136, a baked MMSE table this library does not reproduce). The reference leaves  *
+ * its delay buffer uninitialised for the first block (:218); here that history is zeros.                          */
+typedef struct qdsp_mm qdsp_mm;
+qdsp_mm* qdsp_mm_create(int dtype, float omega, float gainOmega, float muGain, float omegaRelLimit,
+                        const float* interp_taps);
+void qdsp_mm_destroy(qdsp_mm* h);
+int qdsp_mm_set_omega(qdsp_mm* h, float omega, float omegaRelLimit);           /* setOmega, :90-97 (quirk kept)    */
+int qdsp_mm_set_gains(qdsp_mm* h, float gainOmega, float muGain);              /* setGains, :99-104                */
+int qdsp_mm_set_omega_rel_limit(qdsp_mm* h, float omegaRelLimit);              /* setOmegaRelLimit, :106-112       */
+long long qdsp_mm_max_out(qdsp_mm* h, long long count);
+long long qdsp_mm_process(qdsp_mm* h, const void* in_dev, void* out_dev, long long count, const int* blocks, int nblocks,
+                          int block_size, int* out_counts, qdsp_stream_t s);
+/* state[44]: mu, dynOmega, lastOutput, p_0T p_1T p_2T, c_0T c_1T c_2T, nextOffset, delay[0..6] (re, im pairs) */
+int qdsp_mm_get_state(qdsp_mm* h, float state[44]);
+int qdsp_mm_set_state(qdsp_mm* h, const float state[44]);
+
 /* SineSource::run, src/dsp/source.h:55-59: the VOLK rotator over a buffer of ones, i.e. the NCO phasor itself
  * (closed form here); one call produces one block of `count` samples */
 typedef struct qdsp_sinesource qdsp_sinesource;

@@ -425,6 +425,46 @@ class Ref:
 
 
 
+    # -- MMClockRecovery / MSKDemod / PSKDemod ("next" row) ------------------------------------------------
+    def interp_taps(self) -> np.ndarray:
+        t = np.empty((129, 8), np.float32)
+        self.lib.ref_interp_taps.argtypes = [_fp]
+        self.lib.ref_interp_taps(_fptr(t))
+        return t
+
+    def mm(self, x, omega, gain_omega, mu_gain, omega_rel_limit, block):
+        x = np.ascontiguousarray(x)
+        cplx = int(np.iscomplexobj(x))
+        bl = as_blocks(len(x), block)
+        y = np.empty(len(x) + 16, x.dtype)
+        oc = np.zeros(len(bl), np.int32)
+        self.lib.ref_mm.argtypes = [_i, _f, _f, _f, _f, _fp, _ip, _i, _fp, _ip]
+        self.lib.ref_mm.restype = _ll
+        n = self.lib.ref_mm(cplx, omega, gain_omega, mu_gain, omega_rel_limit, _fptr(x.view(np.float32)), _iptr(bl), len(bl),
+                            _fptr(y.view(np.float32)), _iptr(oc))
+        return y[:n].copy(), oc
+
+    def msk_demod(self, fs, dev, baud, x, block):
+        x, px = self._cin(x)
+        bl = as_blocks(len(x), block)
+        y = np.empty(len(x) + 16, np.float32)
+        oc = np.zeros(len(bl), np.int32)
+        self.lib.ref_msk_demod.argtypes = [_f, _f, _f, _fp, _ip, _i, _fp, _ip]
+        self.lib.ref_msk_demod.restype = _ll
+        n = self.lib.ref_msk_demod(fs, dev, baud, px, _iptr(bl), len(bl), _fptr(y), _iptr(oc))
+        return y[:n].copy(), oc
+
+    def psk_demod(self, order, offset, fs, baud, x, block):
+        x, px = self._cin(x)
+        bl = as_blocks(len(x), block)
+        y = np.empty(len(x) + 16, np.complex64)
+        oc = np.zeros(len(bl), np.int32)
+        self.lib.ref_psk_demod.argtypes = [_i, _i, _f, _f, _fp, _ip, _i, _fp, _ip]
+        self.lib.ref_psk_demod.restype = _ll
+        n = self.lib.ref_psk_demod(order, int(offset), fs, baud, px, _iptr(bl), len(bl), _fptr(y.view(np.float32)), _iptr(oc))
+        return y[:n].copy(), oc
+
+
 @lru_cache(maxsize=None)
 def ref(variant: str = "generic") -> Ref:
     return Ref(variant)
@@ -772,6 +812,27 @@ class Port:
         y = np.empty(len(x), np.float32)
         self.lib.port_ssbdemod(fs, bw, mode, px, _iptr(bl), len(bl), _fptr(y))
         return y
+
+    # -- MMClockRecovery ("next" row); `taps` = the caller's INTERP_TAPS[129][8] -------------------------------
+    @staticmethod
+    def mm_initial_state(omega) -> np.ndarray:
+        st = np.zeros(44, np.float32)
+        st[0], st[1] = 0.5, omega   # _mu = 0.5, _dynOmega = _omega (clock_recovery.h:86, 233)
+        return st
+
+    def mm(self, x, omega, gain_omega, mu_gain, omega_rel_limit, taps, block, state=None):
+        x = np.ascontiguousarray(x)
+        cplx = int(np.iscomplexobj(x))
+        taps = np.ascontiguousarray(taps, np.float32)
+        bl = as_blocks(len(x), block)
+        y = np.empty(len(x) + 16, x.dtype)
+        oc = np.zeros(len(bl), np.int32)
+        st = self.mm_initial_state(np.float32(omega)) if state is None else state
+        self.lib.port_mm.argtypes = [_i, _f, _f, _f, _f, _fp, _fp, _ip, _i, _fp, _ip, _fp]
+        self.lib.port_mm.restype = _ll
+        n = self.lib.port_mm(cplx, omega, gain_omega, mu_gain, omega_rel_limit, _fptr(taps), _fptr(x.view(np.float32)),
+                             _iptr(bl), len(bl), _fptr(y.view(np.float32)), _iptr(oc), _fptr(st))
+        return y[:n].copy(), oc
 
 @lru_cache(maxsize=None)
 def port() -> Port:

@@ -684,3 +684,86 @@ void port_ssbdemod(float sampleRate, float bandWidth, int mode, const cf32* x, c
         off += blocks[b];
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * MMClockRecovery<T>::run, src/dsp/clock_recovery.h:127-215 (T = float / complex_t), per run() block.
+ * `taps` is the caller's INTERP_TAPS[129][8] (src/dsp/interpolation_taps.h, a baked MMSE table that
+ * this repository does not reproduce). State layout (floats): [0] mu, [1] dynOmega, [2] lastOutput,
+ * [3..8] p_0T p_1T p_2T (re, im each), [9..14] c_0T c_1T c_2T, [15] nextOffset (as float-encoded int),
+ * [16..29] delay[0..6] (re, im; float streams use the re slots). The reference leaves delay[]
+ * uninitialised for the first block; the oracle (and the product) define it as zeros.
+ * ---------------------------------------------------------------------------------------- */
+#define PORT_STEP(n) (((n) > 0.0f) ? 1.0f : -1.0f)
+long long port_mm(int dtype, float omega, float gainOmega, float muGain, float omegaRelLimit, const float* taps,
+                  const float* x, const int* blocks, int nblocks, float* out, int* out_counts, float* state) {
+    const int es = dtype == 1 ? 2 : 1;                        /* floats per element */
+    const float omegaMin = omega - (omega * omegaRelLimit);   /* :83-84 */
+    const float omegaMax = omega + (omega * omegaRelLimit);
+    float mu = state[0], dynOmega = state[1], lastOutput = state[2];
+    cf32 p0 = {state[3], state[4]}, p1 = {state[5], state[6]}, p2 = {state[7], state[8]};
+    cf32 c0 = {state[9], state[10]}, c1 = {state[11], state[12]}, c2 = {state[13], state[14]};
+    int nextOffset = (int)state[15];
+    float delay[2 * 14];
+    for (int k = 0; k < 14; k++) { delay[2 * k] = state[16 + 2 * k]; delay[2 * k + 1] = state[17 + 2 * k]; }
+    long long off = 0, total = 0;
+    for (int b = 0; b < nblocks; b++) {
+        const int count = blocks[b];
+        const float* in = x + off * es;
+        int outCount = 0;
+        const int maxOut = (int)(2.0f * omega * (float)count);                  /* :135 */
+        for (int k = 0; k < 7 && k < count; k++)                                  /* :138 (the reference copies 7 blindly) */
+            for (int e = 0; e < es; e++) delay[es * (7 + k) + e] = in[es * k + e];
+        int i = nextOffset;
+        for (; i < count && outCount < maxOut;) {
+            const float* t8 = taps + 8 * (int)roundf(mu * 128.0f);
+            const float* src = (i < 7) ? &delay[es * i] : &in[es * (i - 7)];
+            float phaseError;
+            if (dtype == 0) {
+                float outVal = 0.0f;
+                for (int k = 0; k < 8; k++) outVal += src[k] * t8[k];           /* volk_32f_x2_dot_prod_32f, generic */
+                out[total + outCount] = outVal;
+                outCount++;
+                phaseError = (PORT_STEP(lastOutput) * outVal) - (lastOutput * PORT_STEP(outVal));   /* :156 */
+                lastOutput = outVal;
+            } else {
+                p2 = p1; p1 = p0;                                                /* :161-165 */
+                c2 = c1; c1 = c0;
+                float re = 0.0f, im = 0.0f;
+                for (int k = 0; k < 8; k++) { re += src[2 * k] * t8[k]; im += src[2 * k + 1] * t8[k]; }
+                p0.re = re; p0.im = im;
+                out[2 * (total + outCount)] = re;
+                out[2 * (total + outCount) + 1] = im;
+                outCount++;
+                c0.re = PORT_STEP(p0.re); c0.im = PORT_STEP(p0.im);              /* :178 */
+                /* :181  (((p0 - p2) * conj(c1)) - ((c0 - c2) * conj(p1))).re with complex_t's operators (types.h:17-27) */
+                const cf32 a = {p0.re - p2.re, p0.im - p2.im}, bq = {c1.re, -c1.im};
+                const cf32 d = {c0.re - c2.re, c0.im - c2.im}, e = {p1.re, -p1.im};
+                const float ab = (a.re * bq.re) - (a.im * bq.im);
+                const float de = (d.re * e.re) - (d.im * e.im);
+                phaseError = ab - de;
+            }
+            if (phaseError > 1.0f) phaseError = 1.0f;                           /* :185-186 */
+            if (phaseError < -1.0f) phaseError = -1.0f;
+            dynOmega = dynOmega + (gainOmega * phaseError);                     /* :190-192 */
+            if (dynOmega > omegaMax) dynOmega = omegaMax;
+            else if (dynOmega < omegaMin) dynOmega = omegaMin;
+            mu = mu + dynOmega + (muGain * phaseError);                         /* :197-198 */
+            const float roundedStep = floorf(mu);
+            i += (int)roundedStep;                                               /* :201-202 */
+            if (i < 0) i = 0;
+            mu -= roundedStep;                                                   /* :205 */
+        }
+        nextOffset = i - count;                                                  /* :208 */
+        for (int k = 0; k < 7; k++)                                              /* :211 */
+            for (int e = 0; e < es; e++) delay[es * k + e] = (count - 7 + k >= 0) ? in[es * (count - 7 + k) + e] : 0.0f;
+        if (out_counts) out_counts[b] = outCount;
+        total += outCount;
+        off += count;
+    }
+    state[0] = mu; state[1] = dynOmega; state[2] = lastOutput;
+    state[3] = p0.re; state[4] = p0.im; state[5] = p1.re; state[6] = p1.im; state[7] = p2.re; state[8] = p2.im;
+    state[9] = c0.re; state[10] = c0.im; state[11] = c1.re; state[12] = c1.im; state[13] = c2.re; state[14] = c2.im;
+    state[15] = (float)nextOffset;
+    for (int k = 0; k < 14; k++) { state[16 + 2 * k] = delay[2 * k]; state[17 + 2 * k] = delay[2 * k + 1]; }
+    return total;
+}

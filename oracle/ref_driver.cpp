@@ -23,6 +23,8 @@
 #include <dsp/math.h>
 #include <dsp/audio.h>
 #include <dsp/convertion.h>
+#include <dsp/clock_recovery.h>
+#include <new>
 
 #include <chrono>
 #include <thread>
@@ -523,6 +525,71 @@ long long ref_ssbdemod(float sampleRate, float bandWidth, int mode, const float*
     stream<complex_t> s;
     SSBDemod k(&s, sampleRate, bandWidth, mode);
     return run1(&s, k, &k.out, in, blocks, nblocks, out);
+}
+
+// the baked MMSE interpolator table, src/dsp/interpolation_taps.h:6-136 (129 x 8 floats)
+void ref_interp_taps(float* out) { memcpy(out, INTERP_TAPS, sizeof(float) * (INTERP_STEPS + 1) * INTERP_TAP_COUNT); }
+
+}  // extern "C"
+namespace {
+// MMClockRecovery keeps `T delay[1024]` uninitialised (clock_recovery.h:218): construct it in zeroed storage so the
+// first seven outputs are deterministic (the oracle and the product define that history as zeros)
+template <class T>
+long long mm_impl(float omega, float gainOmega, float muGain, float omegaRelLimit, const void* in, const int* blocks,
+                  int nblocks, void* out, int* out_counts) {
+    stream<T> src;
+    void* mem = calloc(1, sizeof(MMClockRecovery<T>));
+    MMClockRecovery<T>* k = new (mem) MMClockRecovery<T>(&src, omega, gainOmega, muGain, omegaRelLimit);
+    k->start();
+    long long n = pump(&src, &k->out, (const T*)in, blocks, nblocks, (T*)out, out_counts, nullptr);
+    k->stop();
+    k->~MMClockRecovery<T>();
+    free(mem);
+    return n;
+}
+template <int ORDER, bool OFFSET>
+long long psk_impl(float sampleRate, float baudRate, const float* in, const int* blocks, int nblocks, float* out,
+                   int* out_counts) {
+    stream<complex_t> src;
+    typedef PSKDemod<ORDER, OFFSET> D;
+    void* mem = calloc(1, sizeof(D));
+    D* d = new (mem) D(&src, sampleRate, baudRate);
+    d->start();
+    long long n = pump(&src, d->out, (const complex_t*)in, blocks, nblocks, (complex_t*)out, out_counts, nullptr);
+    d->stop();
+    d->~D();
+    free(mem);
+    return n;
+}
+}  // namespace
+extern "C" {
+
+// MMClockRecovery<float | complex_t>: src/dsp/clock_recovery.h:68-243
+long long ref_mm(int dtype, float omega, float gainOmega, float muGain, float omegaRelLimit, const float* in,
+                 const int* blocks, int nblocks, float* out, int* out_counts) {
+    return dtype == 1 ? mm_impl<complex_t>(omega, gainOmega, muGain, omegaRelLimit, in, blocks, nblocks, out, out_counts)
+                      : mm_impl<float>(omega, gainOmega, muGain, omegaRelLimit, in, blocks, nblocks, out, out_counts);
+}
+// MSKDemod / PSKDemod<ORDER, OFFSET> hier blocks: src/dsp/demodulator.h:499-682 (defaults of their init())
+long long ref_msk_demod(float sampleRate, float deviation, float baudRate, const float* in, const int* blocks, int nblocks,
+                        float* out, int* out_counts) {
+    stream<complex_t> src;
+    void* mem = calloc(1, sizeof(MSKDemod));
+    MSKDemod* d = new (mem) MSKDemod(&src, sampleRate, deviation, baudRate);
+    d->start();
+    long long n = pump(&src, d->out, (const complex_t*)in, blocks, nblocks, out, out_counts, nullptr);
+    d->stop();
+    d->~MSKDemod();
+    free(mem);
+    return n;
+}
+long long ref_psk_demod(int order, int offset, float sampleRate, float baudRate, const float* in, const int* blocks,
+                        int nblocks, float* out, int* out_counts) {
+    if (order == 2) return psk_impl<2, false>(sampleRate, baudRate, in, blocks, nblocks, out, out_counts);
+    if (order == 4 && !offset) return psk_impl<4, false>(sampleRate, baudRate, in, blocks, nblocks, out, out_counts);
+    if (order == 4) return psk_impl<4, true>(sampleRate, baudRate, in, blocks, nblocks, out, out_counts);
+    if (order == 8) return psk_impl<8, false>(sampleRate, baudRate, in, blocks, nblocks, out, out_counts);
+    return -1;
 }
 
 }  // extern "C"

@@ -249,12 +249,14 @@ class FIR(_Block):
         super().__init__()
         _lib.require_device()
         self.in_dtype = self.out_dtype = np.dtype(dtype).type
-        self.taps = window.createTaps(window.getTapCount())
+        # an even RRC count is rounded up inside createTaps (window.h:186); like the reference's FIR, use the first
+        # getTapCount() taps of what it wrote
+        self.taps = np.ascontiguousarray(window.createTaps(window.getTapCount())[:window.getTapCount()])
         kind = CF32 if self.in_dtype is np.complex64 else F32
         self.h = check(_L().qdsp_fir_create(kind, _fptr(self.taps), len(self.taps)), "qdsp_fir_create")
 
     def updateWindow(self, window: generic_window):  # noqa: N802
-        self.taps = window.createTaps(window.getTapCount())
+        self.taps = np.ascontiguousarray(window.createTaps(window.getTapCount())[:window.getTapCount()])
         check(_L().qdsp_fir_set_taps(self.h, _fptr(self.taps), len(self.taps)), "qdsp_fir_set_taps")
 
     def set_variant(self, v: int):
@@ -1010,4 +1012,126 @@ class SineSource:
             self.close()
         except Exception:
             pass
+
+
+# ---------------------------------------------------------------------------------------------
+# symbol-timing recovery and the PSK / MSK hier blocks (reference clock_recovery.h:68-243, demodulator.h:499-682)
+# ---------------------------------------------------------------------------------------------
+class MMClockRecovery:
+    """dsp::MMClockRecovery<T>: init(in, omega, gainOmega, muGain, omegaRelLimit). `interp_taps` is the reference's
+    INTERP_TAPS[129][8] table (src/dsp/interpolation_taps.h), supplied by the caller. process() returns the recovered
+    symbols; `last_out_counts` holds the per-run()-block counts."""
+
+    def __init__(self, omega, gainOmega, muGain, omegaRelLimit, interp_taps, dtype=np.complex64):
+        _lib.require_device()
+        self.dtype = np.dtype(dtype)
+        t = np.ascontiguousarray(interp_taps, np.float32)
+        if t.shape != (129, 8):
+            raise ValueError("interp_taps must be the 129 x 8 INTERP_TAPS table")
+        self.h = check(_L().qdsp_mm_create(CF32 if self.dtype == np.complex64 else F32, float(omega), float(gainOmega),
+                                           float(muGain), float(omegaRelLimit), _fptr(t)), "qdsp_mm_create")
+        self.last_out_counts = None
+
+    def setOmega(self, omega, omegaRelLimit):  # noqa: N802
+        check(_L().qdsp_mm_set_omega(self.h, float(omega), float(omegaRelLimit)))
+
+    def setGains(self, omegaGain, muGain):  # noqa: N802
+        check(_L().qdsp_mm_set_gains(self.h, float(omegaGain), float(muGain)))
+
+    def setOmegaRelLimit(self, v):  # noqa: N802
+        check(_L().qdsp_mm_set_omega_rel_limit(self.h, float(v)))
+
+    def get_state(self) -> np.ndarray:
+        st = np.zeros(44, np.float32)
+        check(_L().qdsp_mm_get_state(self.h, _fptr(st)))
+        return st
+
+    def set_state(self, st):
+        st = np.ascontiguousarray(st, np.float32)
+        check(_L().qdsp_mm_set_state(self.h, _fptr(st)))
+
+    def max_out(self, n: int) -> int:
+        return int(_L().qdsp_mm_max_out(self.h, int(n)))
+
+    def process_device(self, in_ptr, out_ptr, n, block=None, stream=None) -> int:
+        b, nb, bs = _blocks_arg(n, block)
+        oc = np.zeros(max(_nblocks(n, block), 1), np.int32)
+        m = int(check(_L().qdsp_mm_process(self.h, in_ptr, out_ptr, int(n), _iptr(b), nb, bs, _iptr(oc), stream), "MMClockRecovery"))
+        self.last_out_counts = oc[:_nblocks(n, block)]
+        return m
+
+    def process(self, x, block=None) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=self.dtype)
+        din = DevBuf.from_numpy(x)
+        dout = DevBuf(max(self.max_out(len(x)), 1) * self.dtype.itemsize)
+        m = self.process_device(din.ptr, dout.ptr, len(x), block)
+        y = dout.to_numpy(self.dtype, m)
+        din.free()
+        dout.free()
+        return y
+
+    def close(self):
+        if self.h:
+            _L().qdsp_mm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MSKDemod:
+    """dsp::MSKDemod hier block (demodulator.h:499-565): FloatFMDemod -> MMClockRecovery<float>."""
+
+    def __init__(self, sampleRate, deviation, baudRate, interp_taps, omegaGain=(0.01 * 0.01) / 4, muGain=0.01, omegaRelLimit=0.005):
+        # like the reference constructor, which forwards only (sampleRate, deviation, baudRate) to init() (:503-505)
+        self.demod = FloatFMDemod(sampleRate, deviation)
+        self.recov = MMClockRecovery(np.float32(sampleRate) / np.float32(baudRate), (0.01 * 0.01) / 4, 0.01, 0.005, interp_taps, np.float32)
+
+    def process(self, x, block=None) -> np.ndarray:
+        x = np.ascontiguousarray(x, np.complex64)
+        sizes = [len(x)] if block is None else (list(_as_sizes(len(x), block)))
+        off, parts = 0, []
+        for s in sizes:
+            parts.append(self.demod.process(x[off:off + s]))
+            off += s
+        y = self.recov.process(np.concatenate(parts) if parts else np.empty(0, np.float32), block)
+        self.last_out_counts = self.recov.last_out_counts
+        return y
+
+
+class PSKDemod:
+    """dsp::PSKDemod<ORDER, OFFSET> hier block (demodulator.h:567-682):
+    ComplexAGC(1, 65535, agcRate) -> FIR<complex_t>(RRCTaps) -> CostasLoop<ORDER> [-> DelayImag] -> MMClockRecovery<complex_t>."""
+
+    def __init__(self, order, offset, sampleRate, baudRate, interp_taps, RRCTapCount=32, RRCAlpha=0.32, agcRate=10e-4,
+                 costasLoopBw=0.004, omegaGain=(0.01 * 0.01) / 4, muGain=0.01, omegaRelLimit=0.005):
+        self.agc = ComplexAGC(1.0, 65535.0, agcRate)
+        self.rrc = FIR(RRCTaps(RRCTapCount, sampleRate, baudRate, RRCAlpha))
+        self.demod = CostasLoop(order, costasLoopBw)
+        self.delay = DelayImag() if offset else None
+        self.recov = MMClockRecovery(np.float32(sampleRate) / np.float32(baudRate), omegaGain, muGain, omegaRelLimit, interp_taps)
+
+    def process(self, x, block=None) -> np.ndarray:
+        x = np.ascontiguousarray(x, np.complex64)
+        sizes = [len(x)] if block is None else (list(_as_sizes(len(x), block)))
+        off, parts = 0, []
+        for s in sizes:   # one run() call per block through the sample-rate stages (their state carries in the handles)
+            y = self.demod.process(self.rrc.process(self.agc.process(x[off:off + s])))
+            if self.delay is not None:
+                y = self.delay.process(y)
+            parts.append(y)
+            off += s
+        y = self.recov.process(np.concatenate(parts) if parts else np.empty(0, np.complex64), block)
+        self.last_out_counts = self.recov.last_out_counts
+        return y
+
+
+def _as_sizes(n: int, block):
+    if np.isscalar(block):
+        b = int(block)
+        return [b] * (n // b) + ([n % b] if n % b else [])
+    return [int(v) for v in block]
 

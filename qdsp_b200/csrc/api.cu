@@ -1203,3 +1203,99 @@ long long qdsp_sinesource_process(qdsp_sinesource* h, void* out_dev, long long c
 }
 
 }  // extern "C"
+
+// =================================================================================================
+// MMClockRecovery<float | complex_t> ("next" row), src/dsp/clock_recovery.h:68-243
+// =================================================================================================
+struct qdsp_mm {
+    int dtype = QDSP_CF32;
+    float omega = 1.0f, gainOmega = 0.001f, muGain = 1.0f, rel = 0.005f;
+    float omegaMin = 1.0f, omegaMax = 1.0f;
+    DevState st;             // 44 floats, layout of oracle/port.c port_mm
+    float* taps_dev = nullptr;
+    Partition part;
+    Scratch scratch;         // [nblocks] ints + one long long
+    ~qdsp_mm() {
+        if (taps_dev) cudaFree(taps_dev);
+    }
+};
+
+extern "C" {
+
+qdsp_mm* qdsp_mm_create(int dtype, float omega, float gainOmega, float muGain, float omegaRelLimit,
+                        const float* interp_taps) {
+    if (!interp_taps) {
+        set_last_error("qdsp_mm_create: the 129 x 8 interpolator table is required");
+        return nullptr;
+    }
+    qdsp_mm* h = new (std::nothrow) qdsp_mm();
+    if (!h) return nullptr;
+    h->dtype = dtype;
+    h->omega = omega;
+    h->gainOmega = gainOmega;
+    h->muGain = muGain;
+    h->rel = omegaRelLimit;
+    h->omegaMin = omega - (omega * omegaRelLimit);   // clock_recovery.h:83-84
+    h->omegaMax = omega + (omega * omegaRelLimit);
+    float st[44] = {0};
+    st[0] = 0.5f;    // _mu, clock_recovery.h:234
+    st[1] = omega;   // _dynOmega = _omega, :85
+    if (h->st.init(44, st) != 0 || cudaMalloc(&h->taps_dev, sizeof(float) * 129 * 8) != cudaSuccess ||
+        cudaMemcpy(h->taps_dev, interp_taps, sizeof(float) * 129 * 8, cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_last_error("qdsp_mm_create: device allocation failed");
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+void qdsp_mm_destroy(qdsp_mm* h) { delete h; }
+int qdsp_mm_set_omega(qdsp_mm* h, float omega, float omegaRelLimit) {
+    // MMClockRecovery::setOmega, clock_recovery.h:90-97: the limits are recomputed from the OLD omega and relLimit
+    // members before omega is replaced (a reference quirk, kept); dynOmega restarts at the new omega
+    h->omegaMin = h->omega - (h->omega * h->rel);
+    h->omegaMax = h->omega + (h->omega * h->rel);
+    h->omega = omega;
+    (void)omegaRelLimit;
+    return h->st.set(&omega, 1, 1);
+}
+int qdsp_mm_set_gains(qdsp_mm* h, float gainOmega, float muGain) {   // :99-104
+    h->gainOmega = gainOmega;
+    h->muGain = muGain;
+    return 0;
+}
+int qdsp_mm_set_omega_rel_limit(qdsp_mm* h, float omegaRelLimit) {   // :106-112
+    h->rel = omegaRelLimit;
+    h->omegaMin = h->omega - (h->omega * h->rel);
+    h->omegaMax = h->omega + (h->omega * h->rel);
+    return 0;
+}
+int qdsp_mm_get_state(qdsp_mm* h, float state[44]) { return h->st.get(state, 44); }
+int qdsp_mm_set_state(qdsp_mm* h, const float state[44]) { return h->st.set(state, 44); }
+long long qdsp_mm_max_out(qdsp_mm* h, long long count) {
+    // per run() block the reference caps the output count at 2 * omega * count (:135); with omega >= 1 the loop ends
+    // on the input first: count / omegaMin + 1 symbols per block at most
+    const double per = h->omegaMin > 0.5f ? 1.0 / (double)h->omegaMin : 2.0;
+    return (long long)((double)count * per) + 16;
+}
+long long qdsp_mm_process(qdsp_mm* h, const void* in_dev, void* out_dev, long long count, const int* blocks, int nblocks,
+                          int block_size, int* out_counts, qdsp_stream_t s_) {
+    cudaStream_t s = as_stream(s_);
+    if (h->part.build(count, blocks, nblocks, block_size, 1, 1, s) != 0) return -1;
+    const int nb = h->part.view.nblocks;
+    if (nb == 0) return 0;
+    if (h->scratch.reserve(sizeof(int) * (size_t)nb + 16) != 0) return -1;
+    long long* total_dev = (long long*)h->scratch.p;
+    int* oc_dev = (int*)((char*)h->scratch.p + 8);
+    if (launch_mm(h->dtype == QDSP_CF32, in_dev, h->part, h->taps_dev, h->omega, h->gainOmega, h->muGain, h->omegaMin,
+                  h->omegaMax, h->st.p, out_dev, oc_dev, total_dev, s) != 0)
+        return -1;
+    // the output count is data dependent: this call waits for the kernel
+    long long total = 0;
+    QDSP_CUDA_OK(cudaMemcpyAsync(&total, total_dev, sizeof(total), cudaMemcpyDeviceToHost, s));
+    if (out_counts) QDSP_CUDA_OK(cudaMemcpyAsync(out_counts, oc_dev, sizeof(int) * (size_t)nb, cudaMemcpyDeviceToHost, s));
+    QDSP_CUDA_OK(cudaStreamSynchronize(s));
+    return total;
+}
+
+}  // extern "C"
+

@@ -87,4 +87,9 @@ int launch_sine(float2* out, long long count, uint64_t phase0, uint64_t step, fl
 int launch_ssb(const float2* in, float* out, long long count, uint64_t phase0, uint64_t step, float2 inc1, float2 inc2,
                float2 inc3, cudaStream_t s);
 
+// ---- k_clock.cu: MMClockRecovery (sequential-exact, one warp per stream) --------------------------
+int launch_mm(int cplx, const void* in, const Partition& part, const float* taps_dev, float omega, float gainOmega,
+              float muGain, float omegaMin, float omegaMax, float* state, void* out, int* out_counts_dev,
+              long long* total_dev, cudaStream_t s);
+
 }  // namespace qdsp

@@ -165,6 +165,15 @@ SIGNATURES = {
     "qdsp_ssbdemod_get_phase": (None, [_vp, _fp, _fp]),
     "qdsp_ssbdemod_set_phase": (None, [_vp, _f, _f]),
     "qdsp_ssbdemod_process": (_ll, [_vp, _vp, _vp, _ll, _vp]),
+    "qdsp_mm_create": (_vp, [_i, _f, _f, _f, _f, _fp]),
+    "qdsp_mm_destroy": (None, [_vp]),
+    "qdsp_mm_set_omega": (_i, [_vp, _f, _f]),
+    "qdsp_mm_set_gains": (_i, [_vp, _f, _f]),
+    "qdsp_mm_set_omega_rel_limit": (_i, [_vp, _f]),
+    "qdsp_mm_max_out": (_ll, [_vp, _ll]),
+    "qdsp_mm_process": (_ll, [_vp, _vp, _vp, _ll, _ip, _i, _i, _ip, _vp]),
+    "qdsp_mm_get_state": (_i, [_vp, _fp]),
+    "qdsp_mm_set_state": (_i, [_vp, _fp]),
     "qdsp_sinesource_create": (_vp, [_f, _f]),
     "qdsp_sinesource_destroy": (None, [_vp]),
     "qdsp_sinesource_configure": (_i, [_vp, _f, _f]),

@@ -64,6 +64,13 @@ CASES = {
     "squelch": dict(kind="squelch", level=-30.0, src=("uniform_steps", 50, [1000, 500, 1500], [1.0, 0.001, 0.05]), block=[1000, 500, 1500]),
     "ssb_usb": dict(kind="ssb", fs=48e3, bw=3e3, mode=0, src=("uniform", 51, 0, 3000), block=[1000, 777, 1223]),
     "ssb_lsb": dict(kind="ssb", fs=48e3, bw=3e3, mode=1, src=("uniform", 52, 0, 3000), block=3000),
+    # symbol-timing recovery and the hier demodulators built on it (clock_recovery.h:68-243, demodulator.h:499-682);
+    # 4 samples per symbol, the reference's default loop gains
+    "mm_cf32": dict(kind="mm", omega=4.0, gain_omega=(0.01 * 0.01) / 4, mu_gain=0.01, rel=0.005, src=("qpsk_clean", 61, 0, 20000), block=[8000, 7000, 5000]),
+    "mm_f32": dict(kind="mm", omega=4.0, gain_omega=(0.01 * 0.01) / 4, mu_gain=0.01, rel=0.005, src=("bpsk_real", 62, 0, 16000), block=4000),
+    "msk_demod": dict(kind="msk", fs=48e3, dev=3e3, baud=12e3, src=("msk", 63, 0, 16000), block=[6000, 10000]),
+    "psk_demod4": dict(kind="psk", order=4, offset=0, fs=48e3, baud=12e3, src=("qpsk_rrc", 64, 0, 24000), block=[8000, 16000]),
+    "psk_demod2": dict(kind="psk", order=2, offset=0, fs=48e3, baud=12e3, src=("bpsk_rrc", 65, 0, 16000), block=8000),
     "ssb_dsb": dict(kind="ssb", fs=48e3, bw=3e3, mode=2, src=("uniform", 53, 0, 1000), block=[600, 400]),
 }
 
@@ -87,6 +94,18 @@ def make_input(c, key="src") -> np.ndarray:
         return synth.qpsk_cf32(src[1], src[2], src[3])
     if k == "bpsk":
         return synth.bpsk_cf32(src[1], src[2], src[3])
+    if k == "qpsk_clean":
+        return synth.qpsk_cf32(src[1], src[2], src[3], sps=4, freq_off=0.0, sigma=0.05)
+    if k == "bpsk_real":
+        return np.ascontiguousarray(synth.bpsk_cf32(src[1], src[2], src[3], sps=4, freq_off=0.0, sigma=0.05).real)
+    if k == "msk":   # continuous-phase binary FSK, +-dev, 4 samples per symbol
+        n = np.arange(src[2], src[2] + src[3], dtype=np.int64)
+        bits = 1.0 - 2.0 * (synth._splitmix64((np.uint64(src[1] + 77) << np.uint64(40)) ^ (n // 4).astype(np.uint64)) & np.uint64(1)).astype(np.float64)
+        ph = 2.0 * np.pi * 3e3 / 48e3 * np.cumsum(bits)
+        return (0.8 * np.exp(1j * ph)).astype(np.complex64) + np.float32(0.01) * synth.uniform_cf32(src[1], src[2], src[3])
+    if k in ("qpsk_rrc", "bpsk_rrc"):   # rectangular symbols, small carrier offset: the chain's own RRC does the shaping
+        f = synth.qpsk_cf32 if k == "qpsk_rrc" else synth.bpsk_cf32
+        return f(src[1], src[2], src[3], sps=4, freq_off=0.002, sigma=0.03)
     if k == "uniform_steps":  # uniform noise scaled per run() block
         sizes, gains = src[2], src[3]
         x = synth.uniform_cf32(src[1], 0, int(sum(sizes)))

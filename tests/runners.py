@@ -5,6 +5,13 @@ from oracle import loader
 from tests.cases import make_input
 
 
+def interp_taps():
+    """INTERP_TAPS[129][8] of the reference (src/dsp/interpolation_taps.h), from the committed reference vectors."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors.npz"))
+    return g["interp_taps"]
+
+
 def _stereo(x):
     return np.ascontiguousarray(x).view(np.float32).reshape(-1, 2)
 
@@ -76,6 +83,20 @@ def run_port(c, x):
         return P.squelch(c["level"], x, c["block"]), None
     if k == "ssb":
         return P.ssbdemod(c["fs"], c["bw"], c["mode"], x, c["block"]), None
+    if k == "mm":
+        return P.mm(x, c["omega"], c["gain_omega"], c["mu_gain"], c["rel"], interp_taps(), c["block"])
+    if k == "msk":
+        # MSKDemod = FloatFMDemod -> MMClockRecovery<float> with the constructor's default gains (demodulator.h:503-520)
+        a = P.fm_demod(c["fs"], c["dev"], x)
+        return P.mm(a, float(np.float32(c["fs"]) / np.float32(c["baud"])), (0.01 * 0.01) / 4, 0.01, 0.005, interp_taps(), c["block"])
+    if k == "psk":
+        # PSKDemod<ORDER, false> = ComplexAGC(1, 65535, 1e-3) -> FIR(RRCTaps(32, fs, baud, 0.32)) -> CostasLoop -> MM
+        y = P.complex_agc(1.0, 65535.0, 10e-4, x)
+        # FIR::init asks for 32 taps; RRCTaps::createTaps writes 33 (count | 1, window.h:186) and normalises over all
+        # of them; the filter runs over the first 32 (filter.h:24-27)
+        y = P.fir_cf32(np.ascontiguousarray(P.rrc_taps(32, c["fs"], c["baud"], 0.32)[:32]), y)
+        y = P.costas(c["order"], 0.004, y)[0]
+        return P.mm(y, float(np.float32(c["fs"]) / np.float32(c["baud"])), (0.01 * 0.01) / 4, 0.01, 0.005, interp_taps(), c["block"])
     raise ValueError(k)
 
 
@@ -235,6 +256,19 @@ def run_gpu(c, x, variant=0):
             parts.append(blk.process(x[off:off + s]))
             off += s
         return np.concatenate(parts), None
+    if k == "mm":
+        mm = B.MMClockRecovery(c["omega"], c["gain_omega"], c["mu_gain"], c["rel"], interp_taps(), x.dtype)
+        y = mm.process(x, c["block"])
+        return y, mm.last_out_counts
+    if k == "msk":
+        d = B.MSKDemod(c["fs"], c["dev"], c["baud"], interp_taps())
+        y = d.process(x, c["block"])
+        return y, d.last_out_counts
+    if k == "psk":
+        d = B.PSKDemod(c["order"], c["offset"], c["fs"], c["baud"], interp_taps())
+        d.demod.set_chunking(c.get("chunk", 0), c.get("warmup", 0))
+        y = d.process(x, c["block"])
+        return y, d.last_out_counts
     if k == "costas":
         pl = B.CostasLoop(c["order"], c["bw"])
         pl.set_chunking(c.get("chunk", 0), c.get("warmup", 0))

@@ -39,6 +39,8 @@ def main():
     gold["taps_rational"], gold["id_rational"] = t, np.asarray([i, d], np.int32)
     gold["taps_bandpass"] = R.blackman_bandpass_taps(15e3, 4e3, 19e3, 240e3)
     gold["taps_rrc"] = R.rrc_taps(31, 4.0, 1.0, 0.35)
+    # the reference's baked MMSE interpolator table (src/dsp/interpolation_taps.h), an input of MMClockRecovery
+    gold["interp_taps"] = R.interp_taps()
     # ---- streaming cases ----------------------------------------------------------------------
     for name, c in CASES.items():
         x = make_input(c)
@@ -102,6 +104,15 @@ def main():
             y = R.amdemod(x, c["block"])
         elif k == "squelch":
             y = R.squelch(c["level"], x, c["block"])
+        elif k == "mm":
+            y, oc = R.mm(x, c["omega"], c["gain_omega"], c["mu_gain"], c["rel"], c["block"])
+            gold[name + "_oc"] = oc
+        elif k == "msk":
+            y, oc = R.msk_demod(c["fs"], c["dev"], c["baud"], x, c["block"])
+            gold[name + "_oc"] = oc
+        elif k == "psk":
+            y, oc = R.psk_demod(c["order"], c["offset"], c["fs"], c["baud"], x, c["block"])
+            gold[name + "_oc"] = oc
         elif k == "ssb":
             y = R.ssbdemod(c["fs"], c["bw"], c["mode"], x, c["block"])
         else:
