@@ -1,7 +1,8 @@
 // include/dsp/demodulator.h — FloatFMDemod and FMDemod (reference src/dsp/demodulator.h:33-187). The kernel
 // evaluates the reference's fast_arctan2 phase-difference formula with its exact float sequence (not an
 // atan2 of a conjugate product: SURVEY.md Q6). Also StereoFMDemod, AMDemod and SSBDemod (:189-497); the MSK/PSK
-// hier-block demodulators are not part of this library yet.
+// hier-block demodulators (:499-682) are provided when <dsp/clock_recovery.h> can be included (it needs the
+// reference's interpolation table, see there): define QDSP_WITH_HIER_DEMODS or include clock_recovery.h first.
 #pragma once
 #include <dsp/block.h>
 
@@ -209,3 +210,161 @@ namespace dsp {
         qdsp_ssbdemod* h = nullptr;
     };
 }
+
+#if defined(QDSP_WITH_HIER_DEMODS) || defined(QDSP_INTERP_TAPS)
+#include <dsp/clock_recovery.h>
+#include <dsp/filter.h>
+#include <dsp/pll.h>
+#include <dsp/processing.h>
+#include <dsp/window.h>
+
+namespace dsp {
+    // MSKDemod (reference demodulator.h:499-565): FloatFMDemod -> MMClockRecovery<float>
+    class MSKDemod : public generic_hier_block<MSKDemod> {
+    public:
+        MSKDemod() {}
+        MSKDemod(stream<complex_t>* input, float sampleRate, float deviation, float baudRate, float omegaGain = (0.01 * 0.01) / 4,
+                 float muGain = 0.01f, float omegaRelLimit = 0.005f) {
+            init(input, sampleRate, deviation, baudRate);   // (sic) the reference forwards only these four (:503-505)
+        }
+        void init(stream<complex_t>* input, float sampleRate, float deviation, float baudRate, float omegaGain = (0.01 * 0.01) / 4,
+                  float muGain = 0.01f, float omegaRelLimit = 0.005f) {
+            _sampleRate = sampleRate;
+            _deviation = deviation;
+            _baudRate = baudRate;
+            _omegaGain = omegaGain;
+            _muGain = muGain;
+            _omegaRelLimit = omegaRelLimit;
+            demod.init(input, _sampleRate, _deviation);
+            recov.init(&demod.out, _sampleRate / _baudRate, _omegaGain, _muGain, _omegaRelLimit);
+            out = &recov.out;
+            generic_hier_block<MSKDemod>::registerBlock(&demod);
+            generic_hier_block<MSKDemod>::registerBlock(&recov);
+        }
+        void setSampleRate(float sampleRate) {
+            _sampleRate = sampleRate;
+            demod.setSampleRate(_sampleRate);
+            recov.setOmega(_sampleRate / _baudRate, _omegaRelLimit);
+        }
+        void setDeviation(float deviation) {
+            _deviation = deviation;
+            demod.setDeviation(deviation);
+        }
+        void setBaudRate(float baudRate, float omegaRelLimit) {
+            _baudRate = baudRate;
+            _omegaRelLimit = omegaRelLimit;
+            recov.setOmega(_sampleRate / _baudRate, _omegaRelLimit);
+        }
+        void setMMGains(float omegaGain, float myGain) {
+            _omegaGain = omegaGain;
+            _muGain = myGain;
+            recov.setGains(_omegaGain, _muGain);
+        }
+        void setOmegaRelLimit(float omegaRelLimit) {
+            _omegaRelLimit = omegaRelLimit;
+            recov.setOmegaRelLimit(_omegaRelLimit);
+        }
+
+        stream<float>* out = NULL;
+
+    private:
+        FloatFMDemod demod;
+        MMClockRecovery<float> recov;
+        float _sampleRate = 1, _deviation = 1, _baudRate = 1, _omegaGain = 0, _muGain = 0, _omegaRelLimit = 0;
+    };
+
+    // PSKDemod<ORDER, OFFSET> (reference demodulator.h:567-682):
+    // ComplexAGC(1, 65535, agcRate) -> FIR<complex_t>(RRCTaps) -> CostasLoop<ORDER> [-> DelayImag] -> MMClockRecovery<complex_t>
+    template <int ORDER, bool OFFSET>
+    class PSKDemod : public generic_hier_block<PSKDemod<ORDER, OFFSET>> {
+        using hier = generic_hier_block<PSKDemod<ORDER, OFFSET>>;
+
+    public:
+        PSKDemod() {}
+        PSKDemod(stream<complex_t>* input, float sampleRate, float baudRate, int RRCTapCount = 32, float RRCAlpha = 0.32f,
+                 float agcRate = 10e-4, float costasLoopBw = 0.004f, float omegaGain = (0.01 * 0.01) / 4, float muGain = 0.01f,
+                 float omegaRelLimit = 0.005f) {
+            init(input, sampleRate, baudRate, RRCTapCount, RRCAlpha, agcRate, costasLoopBw, omegaGain, muGain, omegaRelLimit);
+        }
+        void init(stream<complex_t>* input, float sampleRate, float baudRate, int RRCTapCount = 32, float RRCAlpha = 0.32f,
+                  float agcRate = 10e-4, float costasLoopBw = 0.004f, float omegaGain = (0.01 * 0.01) / 4, float muGain = 0.01f,
+                  float omegaRelLimit = 0.005f) {
+            _RRCTapCount = RRCTapCount;
+            _RRCAlpha = RRCAlpha;
+            _sampleRate = sampleRate;
+            _agcRate = agcRate;
+            _costasLoopBw = costasLoopBw;
+            _baudRate = baudRate;
+            _omegaGain = omegaGain;
+            _muGain = muGain;
+            _omegaRelLimit = omegaRelLimit;
+            agc.init(input, 1.0f, 65535, _agcRate);
+            taps.init(_RRCTapCount, _sampleRate, _baudRate, _RRCAlpha);
+            rrc.init(&agc.out, &taps);
+            demod.init(&rrc.out, _costasLoopBw);
+            hier::registerBlock(&agc);
+            hier::registerBlock(&rrc);
+            hier::registerBlock(&demod);
+            if (OFFSET) {
+                delay.init(&demod.out);
+                recov.init(&delay.out, _sampleRate / _baudRate, _omegaGain, _muGain, _omegaRelLimit);
+                hier::registerBlock(&delay);
+            } else {
+                recov.init(&demod.out, _sampleRate / _baudRate, _omegaGain, _muGain, _omegaRelLimit);
+            }
+            hier::registerBlock(&recov);
+            out = &recov.out;
+        }
+        void setInput(stream<complex_t>* input) { agc.setInput(input); }
+        void setSampleRate(float sampleRate) {
+            _sampleRate = sampleRate;
+            taps.setSampleRate(_sampleRate);
+            rrc.updateWindow(&taps);
+            recov.setOmega(_sampleRate / _baudRate, _omegaRelLimit);
+        }
+        void setBaudRate(float baudRate) {
+            _baudRate = baudRate;
+            taps.setBaudRate(_baudRate);
+            rrc.updateWindow(&taps);
+            recov.setOmega(_sampleRate / _baudRate, _omegaRelLimit);
+        }
+        void setRRCParams(int RRCTapCount, float RRCAlpha) {
+            _RRCTapCount = RRCTapCount;
+            _RRCAlpha = RRCAlpha;
+            taps.setTapCount(_RRCTapCount);
+            taps.setAlpha(RRCAlpha);
+            rrc.updateWindow(&taps);
+        }
+        void setAgcRate(float agcRate) {
+            _agcRate = agcRate;
+            agc.setRate(_agcRate);
+        }
+        void setCostasLoopBw(float costasLoopBw) {
+            _costasLoopBw = costasLoopBw;
+            demod.setLoopBandwidth(_costasLoopBw);
+        }
+        void setMMGains(float omegaGain, float myGain) {
+            _omegaGain = omegaGain;
+            _muGain = myGain;
+            recov.setGains(_omegaGain, _muGain);
+        }
+        void setOmegaRelLimit(float omegaRelLimit) {
+            _omegaRelLimit = omegaRelLimit;
+            recov.setOmegaRelLimit(_omegaRelLimit);
+        }
+
+        stream<complex_t>* out = NULL;
+
+    private:
+        dsp::ComplexAGC agc;
+        dsp::RRCTaps taps;
+        dsp::FIR<dsp::complex_t> rrc;
+        CostasLoop<ORDER> demod;
+        DelayImag delay;
+        MMClockRecovery<dsp::complex_t> recov;
+        int _RRCTapCount = 32;
+        float _RRCAlpha = 0.32f, _sampleRate = 1, _agcRate = 1e-3f, _baudRate = 1, _costasLoopBw = 0.004f;
+        float _omegaGain = 0, _muGain = 0, _omegaRelLimit = 0;
+    };
+}
+#endif

@@ -50,29 +50,34 @@ namespace dsp {
         private:
             float _offset = 0;
         };
+    }
 
-        class RRCTaps : public filter_window::generic_window {
-        public:
-            RRCTaps() {}
-            RRCTaps(int tapCount, float sampleRate, float baudRate, float alpha) { init(tapCount, sampleRate, baudRate, alpha); }
-            void init(int tapCount, float sampleRate, float baudRate, float alpha) {
-                _tapCount = tapCount;
-                _sampleRate = sampleRate;
-                _baudRate = baudRate;
-                _alpha = alpha;
-            }
-            int getTapCount() override { return _tapCount; }
-            void setSampleRate(float sampleRate) { _sampleRate = sampleRate; }
-            void setTapCount(int count) { _tapCount = count; }
-            void setBaudRate(float baudRate) { _baudRate = baudRate; }
-            void setAlpha(float alpha) { _alpha = alpha; }
-            void createTaps(float* taps, int tapCount, float factor = 1.0f) override {
-                qdsp_rrc_taps(tapCount, _sampleRate, _baudRate, _alpha, taps);
-            }
+    // (the reference declares RRCTaps in namespace dsp, outside filter_window: window.h:149)
+    class RRCTaps : public filter_window::generic_window {
+    public:
+        RRCTaps() {}
+        RRCTaps(int tapCount, float sampleRate, float baudRate, float alpha) { init(tapCount, sampleRate, baudRate, alpha); }
+        void init(int tapCount, float sampleRate, float baudRate, float alpha) {
+            _tapCount = tapCount;
+            _sampleRate = sampleRate;
+            _baudRate = baudRate;
+            _alpha = alpha;
+        }
+        int getTapCount() override { return _tapCount; }
+        void setSampleRate(float sampleRate) { _sampleRate = sampleRate; }
+        void setTapCount(int count) { _tapCount = count; }
+        void setBaudRate(float baudRate) { _baudRate = baudRate; }
+        void setAlpha(float alpha) { _alpha = alpha; }
+        void createTaps(float* taps, int tapCount, float factor = 1.0f) override {
+            qdsp_rrc_taps(tapCount, _sampleRate, _baudRate, _alpha, taps);
+        }
 
-        private:
-            int _tapCount = 0;
-            float _sampleRate = 1, _baudRate = 1, _alpha = 0.35f;
-        };
+    private:
+        int _tapCount = 0;
+        float _sampleRate = 1, _baudRate = 1, _alpha = 0.35f;
+    };
+
+    namespace filter_window {
+        using dsp::RRCTaps;   // the spelling earlier versions of this header offered
     }
 }

@@ -18,7 +18,21 @@ def _build(qlib):
     subprocess.check_call(cmd)
 
 
+def _write_interp_taps_header(tmp_path):
+    """dsp/clock_recovery.h needs the reference's baked interpolator table (src/dsp/interpolation_taps.h), which this
+    repository does not ship: the test writes a stand-in header from the committed reference vectors."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors.npz"))["interp_taps"]
+    d = tmp_path / "refinc" / "dsp"
+    d.mkdir(parents=True, exist_ok=True)
+    rows = ",\n".join("    { " + ", ".join(f"{v:.9e}f" for v in row) + " }" for row in g)
+    (d / "interpolation_taps.h").write_text(
+        "#pragma once\nconst int INTERP_TAP_COUNT = 8;\nconst int INTERP_STEPS = 128;\n"
+        "const float INTERP_TAPS[INTERP_STEPS + 1][INTERP_TAP_COUNT] = {\n" + rows + "\n};\n")
+    return str(tmp_path / "refinc")
+
+
 def test_headers_compile_and_link(qlib, tmp_path):
+    refinc = _write_interp_taps_header(tmp_path)
     src = tmp_path / "all_headers.cpp"
     src.write_text("""
 #include <dsp/types.h>
@@ -28,7 +42,6 @@ def test_headers_compile_and_link(qlib, tmp_path):
 #include <dsp/filter.h>
 #include <dsp/resampling.h>
 #include <dsp/processing.h>
-#include <dsp/demodulator.h>
 #include <dsp/pll.h>
 #include <dsp/vfo.h>
 #include <dsp/routing.h>
@@ -37,6 +50,9 @@ def test_headers_compile_and_link(qlib, tmp_path):
 #include <dsp/math.h>
 #include <dsp/audio.h>
 #include <dsp/convertion.h>
+#include <dsp/clock_recovery.h>
+#define QDSP_WITH_HIER_DEMODS
+#include <dsp/demodulator.h>
 // the reference's spellings and signatures (SURVEY.md section 8b) must keep compiling
 void wire(dsp::stream<dsp::complex_t>* in, dsp::stream<float>* fin, dsp::stream<dsp::stereo_t>* sin) {
     dsp::filter_window::BlackmanWindow win(300e3f, 75590.55f, 2.4e6f);
@@ -86,12 +102,21 @@ void wire(dsp::stream<dsp::complex_t>* in, dsp::stream<float>* fin, dsp::stream<
     ssb.setBandWidth(2.8e3f); c2s.setInput(fin, &fm.out); (void)s2c.out_left.writeBuf; (void)th.out.readBuf;
     dsp::SineSource sine(1000, 48e3f, 1e3f); sine.setFrequency(2e3f); (void)sine.getBlockSize();
     dsp::FileSink<float> fs(&fm.out, "/dev/null"); (void)fs.isOpen();
+    dsp::MMClockRecovery<dsp::complex_t> mm(in, 4.0f, 2.5e-5f, 0.01f, 0.005f);
+    dsp::MMClockRecovery<float> mmf(fin, 4.0f, 2.5e-5f, 0.01f, 0.005f);
+    dsp::MSKDemod msk(in, 48e3f, 3e3f, 12e3f);
+    dsp::PSKDemod<4, false> psk(in, 48e3f, 12e3f);
+    dsp::PSKDemod<4, true> oqpsk(in, 48e3f, 12e3f);
+    dsp::PSKDemod<2, false> bpsk(in, 48e3f, 12e3f, 31, 0.35f);
+    dsp::RRCTaps rrc(32, 48e3f, 12e3f, 0.32f);
+    mm.setGains(1e-5f, 0.02f); mm.setOmega(4.0f, 0.005f); psk.setCostasLoopBw(0.005f); psk.setMMGains(1e-5f, 0.02f);
+    msk.setDeviation(2.5e3f); (void)psk.out; (void)msk.out; (void)rrc.getTapCount();
     fir.start(); fir.stop();
 }
 int main() { return qdsp_abi_version() == 1 ? 0 : 1; }
 """)
     exe = tmp_path / "all_headers"
-    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I" + os.path.join(ROOT, "include"), str(src),
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I" + os.path.join(ROOT, "include"), "-I" + refinc, str(src),
                            "-L" + os.path.join(ROOT, "qdsp_b200"), "-lqdsp_b200", "-lpthread",
                            "-Wl,-rpath," + os.path.join(ROOT, "qdsp_b200"), "-o", str(exe)])
     assert subprocess.call([str(exe)]) == 0

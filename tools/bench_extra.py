@@ -130,6 +130,17 @@ def main():
             ("Squelch, run() blocks of 1e6 (16 B algorithmic, 24 B moved)", 16, lambda: sq.process_device(xp, yp, n, 1000000, stream=sp)),
             ("SSBDemod", 12, lambda: ssb.process_device(xp, yp, n, stream=sp)),
         ]
+        # Mueller & Mueller clock recovery: sequential-exact, one warp per stream (latency bound by construction)
+        try:
+            taps = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden",
+                                        "reference_vectors.npz"))["interp_taps"]
+            nm = 1 << 22
+            mm = B.MMClockRecovery(4.0, (0.01 * 0.01) / 4, 0.01, 0.005, taps)
+            ms = timed(lambda: mm.process_device(xp, yp, nm, 1000000, stream=sp), 3, warmup=1)
+            print(json.dumps({"config": f"pw MMClockRecovery<complex_t> omega=4, {nm} samples (one stream, sequential-exact)", "ms": ms,
+                              "Msamples_s": nm / ms / 1e3, "Msymbols_s": nm / 4 / ms / 1e3}), flush=True)
+        except Exception as e:  # noqa: BLE001
+            print(json.dumps({"config": "pw MMClockRecovery", "error": str(e)}), flush=True)
         for name, bytes_per, fn in rows:
             ms = timed(fn, args.steps, warmup=1)
             print(json.dumps({"config": f"pw {name}, {n} elements", "ms": ms, "Msamples_s": n / ms / 1e3,
