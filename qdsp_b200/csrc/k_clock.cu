@@ -48,19 +48,33 @@ __global__ void __launch_bounds__(32) mm_kernel(const float* __restrict__ in, Pa
         // first sample comes from the carried delay[] (the previous call's last 7 samples)
         for (int w0 = i / kMmWin * kMmWin; w0 < count; w0 += kMmWin) {
             __syncwarp();
-            for (int e = lane; e < kMmWin + kMmHalo - 1; e += 32) {
-                const long long g = S + w0 - 7 + e;                 // call-relative sample index
-                float2 v = make_float2(0.f, 0.f);
-                if (g >= 0) {
-                    if (g < part.total) {
-                        if (CPLX) v = reinterpret_cast<const float2*>(in)[g];
-                        else v.x = in[g];
+            // 8 loads per lane in flight together (a load-store loop would expose the DRAM latency 128 times per window)
+            for (int e0 = lane; e0 < kMmWin + kMmHalo - 1; e0 += 8 * 32) {
+                float2 v[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int e = e0 + 32 * j;
+                    const long long g = S + w0 - 7 + e;             // call-relative sample index
+                    v[j] = make_float2(0.f, 0.f);
+                    if (e < kMmWin + kMmHalo - 1) {
+                        if (g >= 0) {
+                            if (g < part.total) {
+                                if (CPLX) v[j] = reinterpret_cast<const float2*>(in)[g];
+                                else v[j].x = in[g];
+                            }
+                        } else {
+                            v[j] = make_float2(state[16 + 2 * (int)(g + 7)], state[17 + 2 * (int)(g + 7)]);
+                        }
                     }
-                } else {
-                    v = make_float2(state[16 + 2 * (int)(g + 7)], state[17 + 2 * (int)(g + 7)]);
                 }
-                if (CPLX) reinterpret_cast<float2*>(s_x)[e] = v;
-                else s_x[e] = v.x;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int e = e0 + 32 * j;
+                    if (e < kMmWin + kMmHalo - 1) {
+                        if (CPLX) reinterpret_cast<float2*>(s_x)[e] = v[j];
+                        else s_x[e] = v[j].x;
+                    }
+                }
             }
             __syncwarp();
             if (lane == 0) {
