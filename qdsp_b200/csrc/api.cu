@@ -750,7 +750,9 @@ struct qdsp_ffagc {
 struct qdsp_costas {
     int order = 4;
     float alpha = 0.0f, beta = 0.0f;
-    int chunk = 4096, warmup = 4096;
+    // measured on B200 (2^26 QPSK samples, tools/_costas_sweep.py): (4096, 4096) 38 GS/s, (2048, 2048) 49 GS/s with the same
+    // 4e-6 error against the sequential loop; 1536 warm-up samples: 53 GS/s but 2e-5; 1024: 1e-3 (not merged)
+    int chunk = 2048, warmup = 2048;
     DevState st;   // [4] state + [1] residual
     Scratch scratch;
 };
@@ -1214,7 +1216,10 @@ struct qdsp_mm {
     DevState st;             // 44 floats, layout of oracle/port.c port_mm
     float* taps_dev = nullptr;
     Partition part;
-    Scratch scratch;         // [nblocks] ints + one long long
+    Scratch scratch;         // one long long + one int + [nblocks] ints
+    Scratch spec_scratch;    // speculate-and-verify: per-chunk states, counts, offsets, values, source indices
+    int spec_chunk = 0, spec_warm = 0;   // 0 = sequential-exact single walk
+    int last_rewalked = 0;
     ~qdsp_mm() {
         if (taps_dev) cudaFree(taps_dev);
     }
@@ -1269,6 +1274,16 @@ int qdsp_mm_set_omega_rel_limit(qdsp_mm* h, float omegaRelLimit) {   // :106-112
     h->omegaMax = h->omega + (h->omega * h->rel);
     return 0;
 }
+int qdsp_mm_set_speculation(qdsp_mm* h, int chunk, int warmup) {
+    if (chunk != 0 && (warmup < 0 || chunk < warmup + 8)) {
+        set_last_error("qdsp_mm_set_speculation: need chunk >= warmup + 8");
+        return -1;
+    }
+    h->spec_chunk = chunk;
+    h->spec_warm = warmup;
+    return 0;
+}
+int qdsp_mm_last_rewalked(qdsp_mm* h) { return h->last_rewalked; }
 int qdsp_mm_get_state(qdsp_mm* h, float state[44]) { return h->st.get(state, 44); }
 int qdsp_mm_set_state(qdsp_mm* h, const float state[44]) { return h->st.set(state, 44); }
 long long qdsp_mm_max_out(qdsp_mm* h, long long count) {
@@ -1283,13 +1298,30 @@ long long qdsp_mm_process(qdsp_mm* h, const void* in_dev, void* out_dev, long lo
     if (h->part.build(count, blocks, nblocks, block_size, 1, 1, s) != 0) return -1;
     const int nb = h->part.view.nblocks;
     if (nb == 0) return 0;
-    if (h->scratch.reserve(sizeof(int) * (size_t)nb + 16) != 0) return -1;
+    if (h->scratch.reserve(sizeof(int) * (size_t)nb + 32) != 0) return -1;
     long long* total_dev = (long long*)h->scratch.p;
-    int* oc_dev = (int*)((char*)h->scratch.p + 8);
-    if (launch_mm(h->dtype == QDSP_CF32, in_dev, h->part, h->taps_dev, h->omega, h->gainOmega, h->muGain, h->omegaMin,
-                  h->omegaMax, h->st.p, out_dev, oc_dev, total_dev, s) != 0)
+    int* rewalked_dev = (int*)((char*)h->scratch.p + 8);
+    int* oc_dev = (int*)((char*)h->scratch.p + 16);
+    h->last_rewalked = 0;
+    // speculate and verify: chunks walked in parallel from the default loop state, accepted only where they provably
+    // coincide with the sequential walk (k_clock.cu). Needs omega >= 1 (the reference's 2*omega*count output cap can
+    // then never fire) and at least two chunks.
+    const bool spec = h->spec_chunk > 0 && h->omegaMin >= 1.0f && count >= 2ll * h->spec_chunk;
+    if (spec) {
+        int cap = (int)((double)h->spec_chunk / (double)h->omegaMin) + 4;
+        cap += cap & 1;
+        if (h->spec_scratch.reserve(mm_spec_scratch_bytes(count, h->spec_chunk, cap)) != 0) return -1;
+        if (launch_mm_spec(h->dtype == QDSP_CF32, in_dev, h->part, h->taps_dev, h->gainOmega, h->muGain, h->omegaMin,
+                           h->omegaMax, h->st.p, out_dev, oc_dev, total_dev, rewalked_dev, h->spec_chunk, h->spec_warm, cap,
+                           h->spec_scratch.p, s) != 0)
+            return -1;
+        QDSP_CUDA_OK(cudaMemcpyAsync(&h->last_rewalked, rewalked_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
+    } else if (launch_mm(h->dtype == QDSP_CF32, in_dev, h->part, h->taps_dev, h->omega, h->gainOmega, h->muGain, h->omegaMin,
+                         h->omegaMax, h->st.p, out_dev, oc_dev, total_dev, s) != 0) {
         return -1;
+    }
     // the output count is data dependent: this call waits for the kernel
+    (void)0;
     long long total = 0;
     QDSP_CUDA_OK(cudaMemcpyAsync(&total, total_dev, sizeof(total), cudaMemcpyDeviceToHost, s));
     if (out_counts) QDSP_CUDA_OK(cudaMemcpyAsync(out_counts, oc_dev, sizeof(int) * (size_t)nb, cudaMemcpyDeviceToHost, s));

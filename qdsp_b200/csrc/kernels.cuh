@@ -91,5 +91,9 @@ int launch_ssb(const float2* in, float* out, long long count, uint64_t phase0, u
 int launch_mm(int cplx, const void* in, const Partition& part, const float* taps_dev, float omega, float gainOmega,
               float muGain, float omegaMin, float omegaMax, float* state, void* out, int* out_counts_dev,
               long long* total_dev, cudaStream_t s);
+size_t mm_spec_scratch_bytes(long long count, int chunk, int cap);
+int launch_mm_spec(int cplx, const void* in, const Partition& part, const float* taps_dev, float gainOmega, float muGain,
+                   float omegaMin, float omegaMax, float* state, void* out, int* out_counts_dev, long long* total_dev,
+                   int* rewalked_dev, int chunk, int warm, int cap, void* scratch, cudaStream_t s);
 
 }  // namespace qdsp

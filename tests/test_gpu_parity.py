@@ -572,3 +572,36 @@ def test_psk_demod_chain(name, golden):
     assert e_ref <= 8e-3, e_ref
     # decisions: after lock the recovered symbols sit on the constellation (unit-ish magnitude)
     assert np.median(np.abs(y[1000:])) > 0.5
+
+
+@pytest.mark.parametrize("dtype", ["cf32", "f32"])
+def test_clock_recovery_speculate_and_verify(dtype):
+    # chunks walked in parallel from the default loop state, accepted only where bit-equal at the boundary: symbols,
+    # per-block counts and the carried state must equal the sequential walk's whatever the speculation did -- with a
+    # warm-up long enough to merge (few or no re-walks) and with a hopeless one (every chunk re-walked)
+    from qdsp_b200 import blocks as B, synth
+    from tests.runners import interp_taps
+
+    n = 1 << 18
+    x = synth.qpsk_cf32(91, 0, n, sps=4, freq_off=0.0, sigma=0.05)
+    if dtype == "f32":
+        x = np.ascontiguousarray(x.real)
+    t = interp_taps()
+    args = (4.0, (0.01 * 0.01) / 4, 0.01, 0.005, t, x.dtype)
+    blocks = [100000, 7, 62137, n - 162144]
+    seq = B.MMClockRecovery(*args)
+    y0 = seq.process(x, blocks)
+    oc0, st0 = seq.last_out_counts.copy(), seq.get_state()
+    P = loader.port()
+    yo, oco = P.mm(x, 4.0, (0.01 * 0.01) / 4, 0.01, 0.005, t, blocks)
+    assert np.array_equal(y0.view(np.uint32), yo.view(np.uint32)) and np.array_equal(oc0, oco)
+    for chunk, warm, expect_clean in ((16384, 8192, True), (4096, 64, False)):
+        sp = B.MMClockRecovery(*args)
+        sp.set_speculation(chunk, warm)
+        y = sp.process(x, blocks)
+        assert np.array_equal(y.view(np.uint32), y0.view(np.uint32)), (chunk, warm)
+        assert np.array_equal(sp.last_out_counts, oc0)
+        assert np.array_equal(sp.get_state()[:30].view(np.uint32), st0[:30].view(np.uint32))
+        print(f"MM speculation chunk={chunk} warmup={warm}: {sp.last_rewalked()} of {n // chunk - 1} chunks re-walked")
+        if not expect_clean:
+            assert sp.last_rewalked() > 0

@@ -97,10 +97,10 @@ def main():
         x = uniform(n, 5)
         y = torch.empty(n, dtype=torch.complex64, device="cuda")
         for name, blk, bytes_per in [("BFMDeemp", B.BFMDeemp(48e3, 50e-6), 16), ("ComplexAGC", B.ComplexAGC(1.0, 65535.0, 1e-3), 16),
-                                     ("CostasLoop<4> chunk 4096 warmup 4096", B.CostasLoop(4, 0.004), 16),
+                                     ("CostasLoop<4> chunk 2048 warmup 2048", B.CostasLoop(4, 0.004), 16),
                                      ("FeedForwardAGC", B.FeedForwardAGC(), 16), ("FrequencyXlator", B.FrequencyXlator(FS, -250e3), 16)]:
             if "Costas" in name:
-                blk.set_chunking(4096, 4096)
+                blk.set_chunking(2048, 2048)
             ms = timed(lambda: blk.process_device(x.data_ptr(), y.data_ptr(), n, stream=sp), args.steps, warmup=1)
             print(json.dumps({"config": f"5 {name}, {n} elements", "ms": ms, "Msamples_s": n / ms / 1e3,
                               "hbm_gbs": bytes_per * n / ms / 1e6, "frac_hbm_measured": bytes_per * n / ms / 1e6 / hbm}), flush=True)
@@ -139,6 +139,17 @@ def main():
             ms = timed(lambda: mm.process_device(xp, yp, nm, 1000000, stream=sp), 3, warmup=1)
             print(json.dumps({"config": f"pw MMClockRecovery<complex_t> omega=4, {nm} samples (one stream, sequential-exact)", "ms": ms,
                               "Msamples_s": nm / ms / 1e3, "Msymbols_s": nm / 4 / ms / 1e3}), flush=True)
+            # speculate and verify on real QPSK (the loop has to lock for the chunks to merge), 2^24 samples
+            from qdsp_b200 import synth
+            nq = 1 << 24
+            xq = torch.from_numpy(synth.qpsk_cf32(91, 0, nq, sps=4, freq_off=0.0, sigma=0.05)).cuda()
+            for chunk, warm in ((32768, 8192),):
+                mm2 = B.MMClockRecovery(4.0, (0.01 * 0.01) / 4, 0.01, 0.005, taps)
+                mm2.set_speculation(chunk, warm)
+                ms = timed(lambda: mm2.process_device(xq.data_ptr(), yp, nq, 1000000, stream=sp), 3, warmup=1)
+                print(json.dumps({"config": f"pw MMClockRecovery<complex_t> speculate-and-verify chunk={chunk} warmup={warm}, {nq} QPSK samples",
+                                  "ms": ms, "Msamples_s": nq / ms / 1e3, "Msymbols_s": nq / 4 / ms / 1e3,
+                                  "rewalked_chunks": mm2.last_rewalked(), "chunks": nq // chunk}), flush=True)
         except Exception as e:  # noqa: BLE001
             print(json.dumps({"config": "pw MMClockRecovery", "error": str(e)}), flush=True)
         for name, bytes_per, fn in rows:
