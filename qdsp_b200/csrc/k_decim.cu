@@ -560,7 +560,7 @@ struct SupGeom {
 __device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
 
 template <int Q, int DT, int NSEGT, bool ROT, bool DEMOD, int NSLOTT = 2, int DBG = 0>
-__global__ void __launch_bounds__(160, NSLOTT == 3 ? 3 : 4) decim_sup_kernel(const DecimArgs a) {
+__global__ void __launch_bounds__(NSLOTT == 3 ? 192 : 160, NSLOTT == 3 ? 3 : 4) decim_sup_kernel(const DecimArgs a) {
     using G = SupGeom<Q, DT, NSEGT, NSLOTT>;
     constexpr int D = DT, NSEG = NSEGT, P = G::P;
     constexpr int LEAD = DEMOD ? 1 : 0;
@@ -624,7 +624,9 @@ __global__ void __launch_bounds__(160, NSLOTT == 3 ? 3 : 4) decim_sup_kernel(con
     }
     cta_sync();
 
-    if (warp == 4) {
+    constexpr bool TWO_AUX = NSLOTT == 3;
+    if (warp >= 4) {
+        const int ap = warp - 4;   // TWO_AUX: warp 4 = producer + pass 0, warp 5 = pass 1
         // ================= producer + finisher warp =====================================================
         const long long tile_first = bi.in_start + (long long)(k0 - LEAD) * DSg - a.T - pad + col_off;
         const long long tile_last = tile_first + (long long)(nactive - 1) * L * DSg + (long long)(nsup - 1) * chunk_span + chunk_tail;
@@ -682,6 +684,7 @@ __global__ void __launch_bounds__(160, NSLOTT == 3 ? 3 : 4) decim_sup_kernel(con
         auto finish = [&](int sup, int par) {
 #pragma unroll
             for (int p = 0; p < G::NPASS; p++) {
+                if (TWO_AUX && p != ap) continue;
                 const int fs = p * G::SA + fls;
                 const bool fvalid = fls < G::SA && fs < NSEG;
                 const float4* pb = reinterpret_cast<const float4*>(
@@ -723,13 +726,15 @@ __global__ void __launch_bounds__(160, NSLOTT == 3 ? 3 : 4) decim_sup_kernel(con
             }
         };
 #pragma unroll 1
-        for (int s = 0; s < NSLOT; s++) issue(s, s);
+        if (ap == 0) {
+            for (int s = 0; s < NSLOT; s++) issue(s, s);
+        }
         cta_sync();
         int slot = 0;
 #pragma unroll 1
         for (int sup = 0; sup < nsup; sup++) {
             cta_sync();                  // compute warps are done with slot `slot`; partials of `sup` visible
-            issue(sup + NSLOT, slot);
+            if (ap == 0) issue(sup + NSLOT, slot);
             if (DBG != 2) finish(sup, sup & 1);
             slot = slot == NSLOT - 1 ? 0 : slot + 1;
         }
@@ -954,7 +959,7 @@ static int launch_decim_sup_t(const DecimArgs& a, dim3 grid, cudaStream_t s) {
     auto kern = decim_sup_kernel<Q, DT, NSEGT, ROT, DEMOD, NSLOTT, DBG>;
     constexpr size_t smem = SupGeom<Q, DT, NSEGT, NSLOTT>::smem_bytes;
     QDSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, 160, smem, s>>>(a);
+    kern<<<grid, NSLOTT == 3 ? 192 : 160, smem, s>>>(a);
     QDSP_LAUNCH_OK();
     return 0;
 }
