@@ -263,24 +263,37 @@ fir_decim_kernel(VStream<float2> xs, long long count, long long n_out, const flo
     }
     if (DT) {
         const bool in_aligned = (reinterpret_cast<uintptr_t>(xs.in) & 15) == 0;
-        for (int g = t; g < npairs; g += kFirThreads) {
-            const long long i0 = B + (long long)2 * DT * g;          // even
-            float2 v[2 * (DT ? DT : 1)];
-            if (in_aligned && i0 >= 0 && i0 + 2 * DT <= count) {
-                const float4* src = reinterpret_cast<const float4*>(xs.in + i0);
+        // two units (2 x 2*D samples) per thread in flight together: the tile's ~5 units per thread otherwise expose the
+        // DRAM latency one after the other
+        for (int g0 = t; g0 < npairs; g0 += 2 * kFirThreads) {
+            float2 v[2][2 * (DT ? DT : 1)];
 #pragma unroll
-                for (int j = 0; j < DT; j++) {
-                    const float4 a = ldg_stream128(src + j);
-                    v[2 * j] = make_float2(a.x, a.y);
-                    v[2 * j + 1] = make_float2(a.z, a.w);
+            for (int h = 0; h < 2; h++) {
+                const int g = g0 + h * kFirThreads;
+                const long long i0 = B + (long long)2 * DT * g;      // even
+                if (g < npairs && in_aligned && i0 >= 0 && i0 + 2 * DT <= count) {
+                    const float4* src = reinterpret_cast<const float4*>(xs.in + i0);
+#pragma unroll
+                    for (int j = 0; j < DT; j++) {
+                        const float4 a = ldg_stream128(src + j);
+                        v[h][2 * j] = make_float2(a.x, a.y);
+                        v[h][2 * j + 1] = make_float2(a.z, a.w);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 2 * DT; j++)
+                        v[h][j] = (g < npairs && i0 + j < count) ? xs.at(i0 + j) : make_float2(0.f, 0.f);
                 }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 2 * DT; j++) v[j] = (i0 + j < count) ? xs.at(i0 + j) : make_float2(0.f, 0.f);
             }
 #pragma unroll
-            for (int r = 0; r < DT; r++)   // sub-stream r: elements 2g and 2g+1 are the unit's samples r and D + r
-                sq[(size_t)r * npairs + g] = make_float4(v[r].x, v[DT + r].x, v[r].y, v[DT + r].y);
+            for (int h = 0; h < 2; h++) {
+                const int g = g0 + h * kFirThreads;
+                if (g < npairs) {
+#pragma unroll
+                    for (int r = 0; r < DT; r++)   // sub-stream r: elements 2g and 2g+1 are the unit's samples r and D + r
+                        sq[(size_t)r * npairs + g] = make_float4(v[h][r].x, v[h][DT + r].x, v[h][r].y, v[h][DT + r].y);
+                }
+            }
         }
     } else {
         float* sf = reinterpret_cast<float*>(sq);
