@@ -67,18 +67,19 @@ void fir_plan_destroy(FirPlan* p) {
 }
 
 // a tile of kFirNout outputs parked in shared memory -> global, 128-bit stores when the destination allows
+template <int NT = kFirThreads, int NOUT = kFirNout>
 __device__ __forceinline__ void store_tile(const float2* so, float2* __restrict__ out, long long first, long long limit) {
     const int t = threadIdx.x;
     const long long left = limit - first;
-    const int nvalid = left < kFirNout ? (int)left : kFirNout;
+    const int nvalid = left < NOUT ? (int)left : NOUT;
     float2* dst = out + first;
     if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
         const int nq = nvalid >> 1;
-        for (int q = t; q < nq; q += kFirThreads)
+        for (int q = t; q < nq; q += NT)
             reinterpret_cast<float4*>(dst)[q] = reinterpret_cast<const float4*>(so)[q];
         if (t == 0 && (nvalid & 1)) dst[nvalid - 1] = so[nvalid - 1];
     } else {
-        for (int i = t; i < nvalid; i += kFirThreads) dst[i] = so[i];
+        for (int i = t; i < nvalid; i += NT) dst[i] = so[i];
     }
 }
 
@@ -240,18 +241,19 @@ void fir_decim_plan_destroy(FirDecimPlan* p) {
 
 // DT > 0: compile-time decimation with vectorised staging (one thread moves 2*D consecutive samples = D 128-bit
 // global loads into D sample quads = D 128-bit shared stores); DT == 0: run-time D, scalar staging.
-template <int DT>
-__global__ void __launch_bounds__(kFirThreads, 2)
+template <int DT, int NW>
+__global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 4)
 fir_decim_kernel(VStream<float2> xs, long long count, long long n_out, const float2* __restrict__ taps, int T, int Drt,
                  int U, float2* __restrict__ out) {
     constexpr int R = kFirR;
+    constexpr int NT = NW * 32, NOUT = (NW / 2) * 64 * kFirR;   // threads, outputs per tile
     const int D = DT ? DT : Drt;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int npairs = kFirNout / 2 + U + 8;                         // per sub-stream
+    const int npairs = NOUT / 2 + U + 8;                         // per sub-stream
     float4* sq = reinterpret_cast<float4*>(smem_raw);                 // [D][npairs] sample quads
     float2* st = reinterpret_cast<float2*>(smem_raw + (size_t)D * npairs * 16);  // [D][2][U]
     const int t = threadIdx.x;
-    const long long k_t = (long long)blockIdx.x * kFirNout;           // first output of the tile
+    const long long k_t = (long long)blockIdx.x * NOUT;           // first output of the tile
     // with DT the staged window starts on an even sample index (pad = 0 / 1 samples earlier; the tap tables of that pad
     // are shifted by the same amount)
     const int pad = DT ? (int)(((long long)D * k_t - T) & 1) : 0;
@@ -259,17 +261,17 @@ fir_decim_kernel(VStream<float2> xs, long long count, long long n_out, const flo
 
     {
         const float2* tsrc = taps + (size_t)pad * D * 2 * U;
-        for (int i = t; i < D * 2 * U; i += kFirThreads) st[i] = tsrc[i];
+        for (int i = t; i < D * 2 * U; i += NT) st[i] = tsrc[i];
     }
     if (DT) {
         const bool in_aligned = (reinterpret_cast<uintptr_t>(xs.in) & 15) == 0;
         // two units (2 x 2*D samples) per thread in flight together: the tile's ~5 units per thread otherwise expose the
         // DRAM latency one after the other
-        for (int g0 = t; g0 < npairs; g0 += 2 * kFirThreads) {
+        for (int g0 = t; g0 < npairs; g0 += 2 * NT) {
             float2 v[2][2 * (DT ? DT : 1)];
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                const int g = g0 + h * kFirThreads;
+                const int g = g0 + h * NT;
                 const long long i0 = B + (long long)2 * DT * g;      // even
                 if (g < npairs && in_aligned && i0 >= 0 && i0 + 2 * DT <= count) {
                     const float4* src = reinterpret_cast<const float4*>(xs.in + i0);
@@ -287,7 +289,7 @@ fir_decim_kernel(VStream<float2> xs, long long count, long long n_out, const flo
             }
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                const int g = g0 + h * kFirThreads;
+                const int g = g0 + h * NT;
                 if (g < npairs) {
 #pragma unroll
                     for (int r = 0; r < DT; r++)   // sub-stream r: elements 2g and 2g+1 are the unit's samples r and D + r
@@ -298,17 +300,17 @@ fir_decim_kernel(VStream<float2> xs, long long count, long long n_out, const flo
     } else {
         float* sf = reinterpret_cast<float*>(sq);
         const int nsamp = 2 * npairs * D;                             // consecutive input samples of the tile
-        for (int e0 = t; e0 < nsamp; e0 += 8 * kFirThreads) {
+        for (int e0 = t; e0 < nsamp; e0 += 8 * NT) {
             float2 v[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                const int e = e0 + j * kFirThreads;
+                const int e = e0 + j * NT;
                 const long long i = B + e;
                 v[j] = (e < nsamp && i < count) ? xs.at(i) : make_float2(0.f, 0.f);
             }
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                const int e = e0 + j * kFirThreads;
+                const int e = e0 + j * NT;
                 if (e < nsamp) {
                     const int r = e % D, m = e / D;                   // sub-stream, index within it
                     const int q = m >> 1, h = m & 1;
@@ -352,12 +354,12 @@ fir_decim_kernel(VStream<float2> xs, long long count, long long n_out, const flo
         }
     }
     __syncthreads();
-    float2* so = reinterpret_cast<float2*>(smem_raw);                 // [kFirNout] outputs, then coalesced stores
+    float2* so = reinterpret_cast<float2*>(smem_raw);                 // [NOUT] outputs, then coalesced stores
 #pragma unroll
     for (int i = 0; i < R; i++)
         so[2 * (j0 + i) + parity] = make_float2(accRe[i].x + accRe[i].y, accIm[i].x + accIm[i].y);
     __syncthreads();
-    store_tile(so, out, k_t, n_out);
+    store_tile<NT, NOUT>(so, out, k_t, n_out);
 }
 
 // count input samples (one regular partition: every run() block a multiple of D, so the output grid is uniform)
@@ -365,19 +367,28 @@ int launch_fir_decim(FirDecimPlan* plan, const float2* hist, int H, const float2
                      long long n_out, float2* out, cudaStream_t s) {
     if (n_out <= 0) return 0;
     VStream<float2> xs{hist, in, H};
-    const size_t smem = (size_t)plan->D * (kFirNout / 2 + plan->U + 8) * 16 + (size_t)plan->D * 2 * plan->U * 8;
-    const long long tiles = (n_out + kFirNout - 1) / kFirNout;
-#define QDSP_FIR_DECIM_LAUNCH(DT)                                                                                  \
+    // short sub-filters (config 1b: 32 taps per sub-stream): 128-thread CTAs with 1152-output tiles, 4-5 per SM, overlap one
+    // CTA's staging with the others' math better than 2 x 256 threads; long ones keep the big tile (less halo per output)
+    static const int nw_env = getenv("QDSP_FIR_DECIM_NW") ? atoi(getenv("QDSP_FIR_DECIM_NW")) : 0;
+    const int NW = nw_env == 4 || nw_env == 8 ? nw_env : (plan->U <= 36 ? 4 : 8);
+    const int nout = (NW / 2) * 64 * kFirR;
+    const size_t smem = (size_t)plan->D * (nout / 2 + plan->U + 8) * 16 + (size_t)plan->D * 2 * plan->U * 8;
+    const long long tiles = (n_out + nout - 1) / nout;
+#define QDSP_FIR_DECIM_LAUNCH(DT, NWT)                                                                             \
     {                                                                                                              \
-        QDSP_CUDA_OK(cudaFuncSetAttribute(fir_decim_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); \
-        fir_decim_kernel<DT><<<(unsigned)tiles, kFirThreads, smem, s>>>(xs, count, n_out, plan->taps_dev, plan->T, plan->D, \
-                                                                        plan->U, out);                             \
+        QDSP_CUDA_OK(cudaFuncSetAttribute(fir_decim_kernel<DT, NWT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); \
+        fir_decim_kernel<DT, NWT><<<(unsigned)tiles, NWT * 32, smem, s>>>(xs, count, n_out, plan->taps_dev, plan->T, plan->D, \
+                                                                          plan->U, out);                           \
     }
     static const bool scalar_staging = getenv("QDSP_FIR_DECIM_SCALAR") != nullptr;   // A/B switch
-    if (!scalar_staging && plan->D == 2) QDSP_FIR_DECIM_LAUNCH(2)
-    else if (!scalar_staging && plan->D == 4) QDSP_FIR_DECIM_LAUNCH(4)
-    else if (!scalar_staging && plan->D == 8) QDSP_FIR_DECIM_LAUNCH(8)
-    else QDSP_FIR_DECIM_LAUNCH(0)
+    if (scalar_staging) QDSP_FIR_DECIM_LAUNCH(0, 8)
+    else if (plan->D == 2 && NW == 4) QDSP_FIR_DECIM_LAUNCH(2, 4)
+    else if (plan->D == 2) QDSP_FIR_DECIM_LAUNCH(2, 8)
+    else if (plan->D == 4 && NW == 4) QDSP_FIR_DECIM_LAUNCH(4, 4)
+    else if (plan->D == 4) QDSP_FIR_DECIM_LAUNCH(4, 8)
+    else if (plan->D == 8 && NW == 4) QDSP_FIR_DECIM_LAUNCH(8, 4)
+    else if (plan->D == 8) QDSP_FIR_DECIM_LAUNCH(8, 8)
+    else QDSP_FIR_DECIM_LAUNCH(0, 8)
 #undef QDSP_FIR_DECIM_LAUNCH
     QDSP_LAUNCH_OK();
     return 0;
