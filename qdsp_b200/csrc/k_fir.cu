@@ -83,27 +83,29 @@ __device__ __forceinline__ void store_tile(const float2* so, float2* __restrict_
     }
 }
 
-__global__ void __launch_bounds__(kFirThreads, 2)
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 4)
 fir_dense_kernel(VStream<float2> xs, long long count, const float2* __restrict__ taps, int T, int U,
                  float2* __restrict__ out) {
     constexpr int R = kFirR;
+    constexpr int NT = NW * 32, NOUT = (NW / 2) * 64 * kFirR;   // threads, outputs per tile
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int npairs = kFirNout / 2 + U + 8;
+    const int npairs = NOUT / 2 + U + 8;
     float4* sq = reinterpret_cast<float4*>(smem_raw);                 // [npairs] sample quads
     float2* st = reinterpret_cast<float2*>(smem_raw + (size_t)npairs * 16);  // [2][U] tap pairs
     const int t = threadIdx.x;
-    const long long n_t = (long long)blockIdx.x * kFirNout;           // first output of the tile
+    const long long n_t = (long long)blockIdx.x * NOUT;           // first output of the tile
     const long long B = n_t - (T - 1);                                // sample index of quad 0, element 0
 
     // ---- staging: taps, then the tile's window as (re, re, im, im) quads --------------------------
-    for (int i = t; i < 2 * U; i += kFirThreads) st[i] = taps[i];
+    for (int i = t; i < 2 * U; i += NT) st[i] = taps[i];
     if ((B & 1) == 0 && (reinterpret_cast<uintptr_t>(xs.in) & 15) == 0) {
         // the window starts on an even sample (odd tap counts): one 128-bit load -> one quad, 4 in flight per thread
-        for (int q0 = t; q0 < npairs; q0 += 4 * kFirThreads) {
+        for (int q0 = t; q0 < npairs; q0 += 4 * NT) {
             float4 a[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const int q = q0 + j * kFirThreads;
+                const int q = q0 + j * NT;
                 const long long i0 = B + 2 * (long long)q;
                 if (q < npairs && i0 >= 0 && i0 + 2 <= count) {
                     a[j] = ldg_stream128(reinterpret_cast<const float4*>(xs.in + i0));
@@ -115,7 +117,7 @@ fir_dense_kernel(VStream<float2> xs, long long count, const float2* __restrict__
             }
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const int q = q0 + j * kFirThreads;
+                const int q = q0 + j * NT;
                 if (q < npairs) sq[q] = make_float4(a[j].x, a[j].z, a[j].y, a[j].w);
             }
         }
@@ -123,17 +125,17 @@ fir_dense_kernel(VStream<float2> xs, long long count, const float2* __restrict__
         float* sf = reinterpret_cast<float*>(sq);
         const int nsamp = 2 * npairs;
         // batches of 8 loads per thread in flight together (a one-at-a-time loop exposes the DRAM latency 8x)
-        for (int e0 = t; e0 < nsamp; e0 += 8 * kFirThreads) {
+        for (int e0 = t; e0 < nsamp; e0 += 8 * NT) {
             float2 v[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                const int e = e0 + j * kFirThreads;
+                const int e = e0 + j * NT;
                 const long long i = B + e;
                 v[j] = (e < nsamp && i < count) ? xs.at(i) : make_float2(0.f, 0.f);
             }
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                const int e = e0 + j * kFirThreads;
+                const int e = e0 + j * NT;
                 if (e < nsamp) {
                     const int q = e >> 1, h = e & 1;
                     sf[4 * q + h] = v[j].x;
@@ -177,12 +179,12 @@ fir_dense_kernel(VStream<float2> xs, long long count, const float2* __restrict__
     // ---- store: outputs n = n_t + 2*(j0 + i) + parity. A thread's outputs are 16 bytes apart and the lanes 144:
     // exchange them through the (now dead) sample window so that the tile leaves as coalesced 128-bit stores ----
     __syncthreads();
-    float2* so = reinterpret_cast<float2*>(smem_raw);                 // [kFirNout], 18 KB <= the window's footprint
+    float2* so = reinterpret_cast<float2*>(smem_raw);                 // [NOUT], 18 KB <= the window's footprint
 #pragma unroll
     for (int i = 0; i < R; i++)
         so[2 * (j0 + i) + parity] = make_float2(accRe[i].x + accRe[i].y, accIm[i].x + accIm[i].y);
     __syncthreads();
-    store_tile(so, out, n_t, count);
+    store_tile<NT, NOUT>(so, out, n_t, count);
 }
 
 // =================================================================================================
@@ -402,14 +404,20 @@ int launch_fir_dense(FirPlan* plan, const float2* hist, int H, const float2* in,
         return -1;
     }
     VStream<float2> xs{hist, in, H};
-    const size_t smem = ((size_t)kFirNout / 2 + plan->U + 8) * 16 + (size_t)2 * plan->U * 8;
-    static bool attr_set = false;
-    if (!attr_set) {
-        QDSP_CUDA_OK(cudaFuncSetAttribute(fir_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-        attr_set = true;
+    // short filters (config 1a: 127 taps): 128-thread CTAs with 1152-output tiles, 5 per SM; long ones keep the 2304-output
+    // tile (the window's T-1 halo is staged once per tile)
+    static const int nw_env = getenv("QDSP_FIR_NW") ? atoi(getenv("QDSP_FIR_NW")) : 0;
+    const int NW = nw_env == 4 || nw_env == 8 ? nw_env : (plan->U <= 144 ? 4 : 8);
+    const int nout = (NW / 2) * 64 * kFirR;
+    const size_t smem = ((size_t)nout / 2 + plan->U + 8) * 16 + (size_t)2 * plan->U * 8;
+    const long long tiles = (count + nout - 1) / nout;
+    if (NW == 4) {
+        QDSP_CUDA_OK(cudaFuncSetAttribute(fir_dense_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        fir_dense_kernel<4><<<(unsigned)tiles, 128, smem, s>>>(xs, count, plan->taps_dev, plan->T, plan->U, out);
+    } else {
+        QDSP_CUDA_OK(cudaFuncSetAttribute(fir_dense_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        fir_dense_kernel<8><<<(unsigned)tiles, 256, smem, s>>>(xs, count, plan->taps_dev, plan->T, plan->U, out);
     }
-    const long long tiles = (count + kFirNout - 1) / kFirNout;
-    fir_dense_kernel<<<(unsigned)tiles, kFirThreads, smem, s>>>(xs, count, plan->taps_dev, plan->T, plan->U, out);
     QDSP_LAUNCH_OK();
     return 0;
 }
