@@ -45,6 +45,7 @@ struct DecimArgs {
     PartitionDev part;
     int T, D, P, NSEG, R, NSTAGE, NSUP, L;
     int DS, nslices;     // global row stride (full decimation) and column slices per row (1 = unsliced)
+    int plane_fast;      // grid = (planes, tiles, blocks) instead of (tiles, blocks, planes): see launch_decim
     const NcoDev* nco;
     long long abs0;
     float phasor_speed;
@@ -136,13 +137,14 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
     const int NSEG = NSEGT ? NSEGT : a.NSEG;     // all shared-memory offsets fold into immediates
     const int P = D / 2, L = a.L;
     const int t = threadIdx.x;
-    const int b = blockIdx.y;
-    const int ch = blockIdx.z / a.nslices, slice = blockIdx.z - ch * a.nslices;
-    const int plane = blockIdx.z;                // output plane: channel, or (channel, slice) for sliced rows
+    const int tile_x = a.plane_fast ? blockIdx.y : blockIdx.x;
+    const int b = a.plane_fast ? blockIdx.z : blockIdx.y;
+    const int plane = a.plane_fast ? blockIdx.x : blockIdx.z;   // output plane: channel, or (channel, slice) for sliced rows
+    const int ch = plane / a.nslices, slice = plane - ch * a.nslices;
     const int DSg = a.DS;                        // global row stride; == D unless the rows are sliced
     const long long col_off = (long long)slice * D;
     const BlkInfo bi = a.part.get(b);
-    const int k0 = blockIdx.x * (NSEG * L);
+    const int k0 = tile_x * (NSEG * L);
     if (k0 >= bi.out_count) return;
 
     // ---- shared memory carve-up (byte offsets from the dynamic base) ---------------------------
@@ -209,7 +211,7 @@ __global__ void __launch_bounds__(MAXT, MINB) decim_kernel(const DecimArgs a) {
     }
     // leading-angle override of the block's very first output (warp 0)
     bool use_override = false;
-    if (DEMOD && blockIdx.x == 0) {
+    if (DEMOD && tile_x == 0) {
         int pb = b - 1;
         BlkInfo pbi{};
         while (pb >= 0) {
@@ -570,13 +572,14 @@ __global__ void __launch_bounds__(NSLOTT == 3 ? 192 : 160, NSLOTT == 3 ? 3 : 4) 
     const int L = a.L;
     const int t = threadIdx.x;
     const int warp = t >> 5, lane = t & 31;
-    const int b = blockIdx.y;
-    const int ch = blockIdx.z / a.nslices, slice = blockIdx.z - ch * a.nslices;
-    const int plane = blockIdx.z;
+    const int tile_x = a.plane_fast ? blockIdx.y : blockIdx.x;
+    const int b = a.plane_fast ? blockIdx.z : blockIdx.y;
+    const int plane = a.plane_fast ? blockIdx.x : blockIdx.z;
+    const int ch = plane / a.nslices, slice = plane - ch * a.nslices;
     const int DSg = a.DS;
     const long long col_off = (long long)slice * D;
     const BlkInfo bi = a.part.get(b);
-    const int k0 = blockIdx.x * (NSEG * L);
+    const int k0 = tile_x * (NSEG * L);
     if (k0 >= bi.out_count) return;
 
     const long long chunk_span = (long long)Q * DSg;               // global samples one stage advances
@@ -602,7 +605,7 @@ __global__ void __launch_bounds__(NSLOTT == 3 ? 192 : 160, NSLOTT == 3 ? 3 : 4) 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     bool use_override = false;
-    if (DEMOD && blockIdx.x == 0) {
+    if (DEMOD && tile_x == 0) {
         int pb = b - 1;
         BlkInfo pbi{};
         while (pb >= 0) {
@@ -1005,6 +1008,12 @@ int launch_decim(DecimPlan* plan, const float2* hist, int H, const float2* in, c
     a.out_stride = out_stride;
     const int per_tile = a.NSEG * a.L;
     dim3 grid((part.max_out + per_tile - 1) / per_tile, part.view.nblocks, nch * plan->nslices);
+    // several planes (channels x column slices) read the same input: make the plane the fastest grid dimension so that
+    // the CTAs resident together are the planes of the same few input tiles -- the tile is fetched from DRAM once and the
+    // other planes hit L2 (config 4, 32 channels: 3.98 GB -> see DESIGN.md of DRAM reads per 134 MB of input)
+    static const bool pf_env = getenv("QDSP_DECIM_PLANE_FAST") ? atoi(getenv("QDSP_DECIM_PLANE_FAST")) != 0 : true;
+    a.plane_fast = pf_env && nch * plan->nslices > 1 && grid.x <= 65535 && grid.y <= 65535;
+    if (a.plane_fast) grid = dim3(nch * plan->nslices, grid.x, grid.y);
     const size_t stage_bytes = (size_t)a.NSEG * (a.R * a.D + decim_seg_pad(a.D)) * sizeof(float2);
     const size_t smem_stage = (size_t)a.NSTAGE * stage_bytes + (size_t)2 * a.NSEG * a.R * (a.P | 1) * sizeof(float2) +
                               (size_t)a.NSEG * (a.L + 1) * sizeof(float2) + 16 + a.NSTAGE * 8 + 64 +
