@@ -173,6 +173,10 @@ int qdsp_vfofm_history_len(qdsp_vfofm* h);
  * stream; kernel_ms() synchronises and returns the last launch's device time */
 int qdsp_vfofm_enable_timing(qdsp_vfofm* h, int on);
 double qdsp_vfofm_kernel_ms(qdsp_vfofm* h);
+/* the same with one event pair per launch (round robin over `pairs`), so a whole timed region can be bracketed without a
+ * synchronisation between launches; kernel_ms_mean() synchronises and averages the launches recorded since enable */
+int qdsp_vfofm_enable_timing_ring(qdsp_vfofm* h, int pairs);
+double qdsp_vfofm_kernel_ms_mean(qdsp_vfofm* h, int* launches);
 
 /* ---- channelizer: nch x [VFO -> FloatFMDemod] off one Splitter (routing.h:47-57) ------------ */
 typedef struct qdsp_channelizer qdsp_channelizer;

@@ -458,7 +458,9 @@ struct qdsp_channelizer {
     size_t stage_samples = 0;
     // bench hook: events around the dominant kernel
     bool timing = false;
-    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;          // the current launch's pair (= ring[ring_pos])
+    std::vector<cudaEvent_t> ring0, ring1;                  // one pair per launch, round robin (bench: whole timed region)
+    long long ring_launches = 0;
 
     int upload_nco() {
         std::vector<NcoDev> v(nch);
@@ -509,7 +511,14 @@ struct qdsp_channelizer {
         const float* din = demod.p + (size_t)cur * nch;
         float* dout = demod.p + (size_t)(cur ^ 1) * nch;
         int rc;
-        if (timing) QDSP_CUDA_OK(cudaEventRecord(ev_k0, s));
+        if (timing) {
+            if (!ring0.empty()) {
+                ev_k0 = ring0[ring_launches % (long long)ring0.size()];
+                ev_k1 = ring1[ring_launches % (long long)ring1.size()];
+                ring_launches++;
+            }
+            QDSP_CUDA_OK(cudaEventRecord(ev_k0, s));
+        }
         if (plan && variant != 1)
             rc = launch_decim(plan, (const float2*)hist.ptr(), hist.H, (const float2*)in_dev, part, 1, nco_dev,
                               abs_pos, nch, phasor_speed, din, dout, (float2*)iq, audio, out_stride, s);
@@ -535,8 +544,12 @@ struct qdsp_channelizer {
             if (ev_done[i]) cudaEventDestroy(ev_done[i]);
         }
         if (copy_stream) cudaStreamDestroy(copy_stream);
-        if (ev_k0) cudaEventDestroy(ev_k0);
-        if (ev_k1) cudaEventDestroy(ev_k1);
+        if (ring0.empty()) {
+            if (ev_k0) cudaEventDestroy(ev_k0);
+            if (ev_k1) cudaEventDestroy(ev_k1);
+        }
+        for (cudaEvent_t e : ring0) cudaEventDestroy(e);
+        for (cudaEvent_t e : ring1) cudaEventDestroy(e);
     }
 };
 struct qdsp_vfofm {
@@ -672,6 +685,39 @@ int qdsp_vfofm_enable_timing(qdsp_vfofm* h, int on) {
     }
     h->c.timing = on != 0;
     return 0;
+}
+int qdsp_vfofm_enable_timing_ring(qdsp_vfofm* h, int pairs) {
+    if (pairs < 1) return -1;
+    if (h->c.ring0.empty() && h->c.ev_k0) {
+        cudaEventDestroy(h->c.ev_k0);
+        cudaEventDestroy(h->c.ev_k1);
+    }
+    for (cudaEvent_t e : h->c.ring0) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->c.ring1) cudaEventDestroy(e);
+    h->c.ring0.assign(pairs, nullptr);
+    h->c.ring1.assign(pairs, nullptr);
+    for (int i = 0; i < pairs; i++) {
+        QDSP_CUDA_OK(cudaEventCreate(&h->c.ring0[i]));
+        QDSP_CUDA_OK(cudaEventCreate(&h->c.ring1[i]));
+    }
+    h->c.ev_k0 = h->c.ring0[0];
+    h->c.ev_k1 = h->c.ring1[0];
+    h->c.ring_launches = 0;
+    h->c.timing = true;
+    return 0;
+}
+double qdsp_vfofm_kernel_ms_mean(qdsp_vfofm* h, int* launches) {
+    const long long n = h->c.ring_launches < (long long)h->c.ring0.size() ? h->c.ring_launches : (long long)h->c.ring0.size();
+    if (launches) *launches = (int)n;
+    if (n <= 0) return -1.0;
+    double sum = 0.0;
+    for (long long i = 0; i < n; i++) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(h->c.ring1[i]) != cudaSuccess) return -1.0;
+        if (cudaEventElapsedTime(&ms, h->c.ring0[i], h->c.ring1[i]) != cudaSuccess) return -1.0;
+        sum += ms;
+    }
+    return sum / (double)n;
 }
 double qdsp_vfofm_kernel_ms(qdsp_vfofm* h) {
     if (!h->c.ev_k0) return -1.0;

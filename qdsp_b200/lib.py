@@ -108,6 +108,8 @@ SIGNATURES = {
     "qdsp_vfofm_import_tail": (_i, [_vp, _vp, _i, _vp]),
     "qdsp_vfofm_history_len": (_i, [_vp]),
     "qdsp_vfofm_enable_timing": (_i, [_vp, _i]),
+    "qdsp_vfofm_enable_timing_ring": (_i, [_vp, _i]),
+    "qdsp_vfofm_kernel_ms_mean": (_d, [_vp, _ip]),
     "qdsp_vfofm_kernel_ms": (_d, [_vp]),
     "qdsp_channelizer_create": (_vp, [_i, _fp, _f, _f, _f, _f]),
     "qdsp_channelizer_destroy": (None, [_vp]),
