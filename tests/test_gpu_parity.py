@@ -605,3 +605,16 @@ def test_clock_recovery_speculate_and_verify(dtype):
         print(f"MM speculation chunk={chunk} warmup={warm}: {sp.last_rewalked()} of {n // chunk - 1} chunks re-walked")
         if not expect_clean:
             assert sp.last_rewalked() > 0
+
+
+def test_agc_unaligned_blocks():
+    # run() blocks that start off the 16-byte grid take the scalar head / tail of the 128-bit max and scale passes
+    from qdsp_b200 import blocks as B, synth
+
+    P = loader.port()
+    x = synth.uniform_f32(66, 0, 20011)
+    blocks = [1001, 3, 4999, 1, 7003, 7004]
+    y = B.AGC(20.0, 48e3).process(x, blocks)
+    yo = P.agc(20.0, 48e3, x, blocks)
+    assert y.shape == yo.shape
+    assert np.max(np.abs(y - yo)) <= 1e-6 * max(1.0, float(np.max(np.abs(yo))))
