@@ -618,3 +618,20 @@ def test_agc_unaligned_blocks():
     yo = P.agc(20.0, 48e3, x, blocks)
     assert y.shape == yo.shape
     assert np.max(np.abs(y - yo)) <= 1e-6 * max(1.0, float(np.max(np.abs(yo))))
+
+
+def test_channelizer_ragged_partition_plane_fast_grid():
+    # several channels + an explicit (ragged) run() partition: the plane-fastest grid order must decode tile / block /
+    # channel the same way as the default order (QDSP_DECIM_PLANE_FAST=0 is the A/B switch of the launcher)
+    from qdsp_b200 import blocks as B
+
+    c = CASES["channelizer"]
+    x = make_input(c)
+    blocks = [16384, 128 * 77, 0, 128 * 51, len(x) - 16384 - 128 * 128]
+    ch = B.Channelizer(c["offsets"], c["in_sr"], c["out_sr"], c["bw"], c["dev"])
+    y = ch.process(x, blocks)
+    P = loader.port()
+    rows = [P.vfo_fm(o, c["in_sr"], c["out_sr"], c["bw"], c["dev"], x, blocks)[0] for o in c["offsets"]]
+    yo = np.stack(rows)
+    assert y.shape == yo.shape
+    assert np.max(np.abs(y[:, 16:] - yo[:, 16:])) <= AUDIO_TOL
