@@ -284,8 +284,8 @@ def ours(args):
     k_ms = float(np.mean(kernel_ms))
     achieved = ALG_BYTES_PER_SAMPLE * n / (k_ms * 1e-3) / 1e9
     # DRAM bytes per launch of the fused kernel at the default workload, from the committed ncu --set full capture
-    # (profiles/r01_fused_vfofm_v2_ncu_full.txt: dram__bytes_read.sum 2.227204 GB + dram__bytes_write.sum 26.41 MB)
-    traffic = 2.227204e9 + 26.410752e6 if n == N_SAMPLES else None
+    # (profiles/r01_fused_vfofm_final_ncu_full.txt: dram__bytes_read.sum 2.264114 GB + dram__bytes_write.sum 26.07 MB)
+    traffic = 2.264114e9 + 26.067968e6 if n == N_SAMPLES else None
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic, "peak_source": peak_src, "kernel": "qdsp::decim_sup_kernel<9,50,5,ROT,DEMOD> (fused xlate+resample+demod)",
             "kernel_ms": k_ms, "alg_bytes_per_launch": ALG_BYTES_PER_SAMPLE * n,
