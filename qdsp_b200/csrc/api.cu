@@ -519,7 +519,17 @@ struct qdsp_channelizer {
             }
             QDSP_CUDA_OK(cudaEventRecord(ev_k0, s));
         }
-        if (plan && variant != 1)
+        bool hist_folded = false;
+        int rpad = -1;
+        if (plan && variant != 1 && nch == 1 && rowlane_supported(plan) && (reinterpret_cast<uintptr_t>(in_dev) & 15) == 0 &&
+            part.max_out > 0 && (rpad = rowlane_uniform_pad(part, T)) >= 0) {
+            // row-per-lane kernel; the history advance (resampling.h:129) is folded into its first CTA
+            const NcoDev nh{nco[0].phase, nco[0].step};
+            rc = launch_decim_rowlane(plan, taps.data(), (const float2*)hist.ptr(), (float2*)hist.buf[hist.cur ^ 1], hist.H,
+                                      (const float2*)in_dev, part, 1, nco_dev, &nh, abs_pos, phasor_speed, din, dout,
+                                      (float2*)iq, audio, rpad, s);
+            hist_folded = rc == 0;
+        } else if (plan && variant != 1)
             rc = launch_decim(plan, (const float2*)hist.ptr(), hist.H, (const float2*)in_dev, part, 1, nco_dev,
                               abs_pos, nch, phasor_speed, din, dout, (float2*)iq, audio, out_stride, s);
         else
@@ -529,7 +539,8 @@ struct qdsp_channelizer {
         if (rc != 0) return -1;
         if (timing) QDSP_CUDA_OK(cudaEventRecord(ev_k1, s));
         if (part.total_out > 0) cur ^= 1;
-        if (hist.advance(in_dev, count, s) != 0) return -1;
+        if (hist_folded) hist.cur ^= 1;
+        else if (hist.advance(in_dev, count, s) != 0) return -1;
         abs_pos += count;
         return part.total_out;
     }

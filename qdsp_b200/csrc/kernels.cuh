@@ -44,6 +44,14 @@ int launch_decim(DecimPlan* plan, const float2* hist, int H, const float2* in, c
                  const NcoDev* nco, long long abs0, int nch, float phasor_speed, const float* demod_in,
                  float* demod_out, float2* out_iq, float* audio, long long out_stride, cudaStream_t s);
 
+// ---- k_rowlane.cu: row-per-lane decimating FIR (narrow rows, one channel), folds the history advance ----
+bool rowlane_supported(const DecimPlan* plan);
+int rowlane_uniform_pad(const Partition& part, int T);
+int launch_decim_rowlane(DecimPlan* plan, const float* taps_host, const float2* hist, float2* hist_next, int H,
+                         const float2* in, const Partition& part, int mode, const NcoDev* nco_dev, const NcoDev* nco_host,
+                         long long abs0, float phasor_speed, const float* demod_in, float* demod_out, float2* out_iq,
+                         float* audio, int pad, cudaStream_t s);
+
 // ---- k_fir.cu: register-blocked dense FIR (cf32, D = 1) -----------------------------------------
 struct FirPlan;
 FirPlan* fir_plan_create(const float* taps, int T);

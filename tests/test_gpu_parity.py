@@ -635,3 +635,55 @@ def test_channelizer_ragged_partition_plane_fast_grid():
     yo = np.stack(rows)
     assert y.shape == yo.shape
     assert np.max(np.abs(y[:, 16:] - yo[:, 16:])) <= AUDIO_TOL
+
+
+# ---- round 2: row-per-lane fused kernel (k_rowlane.cu) ---------------------------------------------------------
+@pytest.mark.parametrize("block", [819200 // 8, [10000, 7778, 50, 0, 52, 20002, 12140, 40], [100, 100, 100], 1600, [48, 2, 16000, 35168]])
+def test_rowlane_fused_chain_partitions(block):
+    # the row-per-lane kernel takes batches whose run() blocks start on even samples (uniform tap-table pad):
+    # tiles that start in the history, ragged tails, tiny blocks, blocks off the decimation grid (leading-angle
+    # override), several tiles per block -- against the oracle (f64 NCO) and against the generic kernel
+    from qdsp_b200 import blocks as B, synth
+
+    P = loader.port()
+    n = int(sum(block)) if isinstance(block, list) else 204800
+    x = synth.cfg2_input(0, n)
+    v = B.VFOFM(250e3, 2.4e6, 48e3, 48e3, 5e3)
+    v.want_iq = True
+    y = v.process(x, block)
+    iq = v.last_iq
+    oc = v.last_out_counts
+    a64, oc64, iq64 = P.vfo_fm(250e3, 2.4e6, 48e3, 48e3, 5e3, x, block, nco_f64=True, want_iq=True)
+    assert np.array_equal(np.asarray(oc, np.int32), np.asarray(oc64, np.int32))
+    assert y.shape == a64.shape and iq.shape == iq64.shape
+    if len(iq64):
+        assert rel_l2(iq, iq64) <= IQ_TOL, rel_l2(iq, iq64)
+    g = B.VFOFM(250e3, 2.4e6, 48e3, 48e3, 5e3)
+    g.set_variant(1)
+    yg = g.process(x, block)
+    # audio: away from the start-up (zero history: |y| ~ 0, the angle of rounding noise) <= 1e-4; the head is pinned
+    # through the resampled IQ above and a looser absolute bound here
+    assert np.abs(y[16:] - a64[16:]).max(initial=0) <= AUDIO_TOL, np.abs(y[16:] - a64[16:]).max()
+    assert np.abs(y[16:] - yg[16:]).max(initial=0) <= AUDIO_TOL
+    assert np.abs(y[:16] - a64[:16]).max(initial=0) <= 0.5
+
+
+def test_rowlane_streaming_calls_carry_history_and_phase():
+    # several process() calls (history tail advanced inside the kernel, demod phase + NCO position carried)
+    from qdsp_b200 import blocks as B, synth
+
+    x = synth.cfg2_input(0, 409600)
+    one = B.VFOFM(250e3, 2.4e6, 48e3, 48e3, 5e3).process(x, 8192)
+    v = B.VFOFM(250e3, 2.4e6, 48e3, 48e3, 5e3)
+    cuts = [0, 8192 * 3, 8192 * 3 + 200, 8192 * 3 + 200 + 8192 * 20, len(x)]   # a 200-sample call: count < history
+    many = np.concatenate([v.process(x[a:b], 8192) for a, b in zip(cuts[:-1], cuts[1:])])
+    ref = np.concatenate([B.VFOFM(250e3, 2.4e6, 48e3, 48e3, 5e3).process(x[:cuts[1]], 8192)])
+    assert np.abs(many[:len(ref)] - ref).max() <= 1e-6
+    P = loader.port()
+    sizes = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        sizes += [int(s) for s in loader.as_blocks(b - a, 8192)]
+    a64, _ = P.vfo_fm(250e3, 2.4e6, 48e3, 48e3, 5e3, x, sizes, nco_f64=True)
+    assert many.shape == a64.shape
+    assert np.abs(many[16:] - a64[16:]).max() <= AUDIO_TOL
+    assert one.shape[0] > 0
