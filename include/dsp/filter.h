@@ -79,8 +79,9 @@ namespace dsp {
             generic_block<BFMDeemp>::registerOutput(&out);
         }
         void setInput(stream<stereo_t>* in) { generic_block<BFMDeemp>::rebindInput(_in, in); }
-        void setSampleRate(float sampleRate) { _sampleRate = sampleRate; rebuild(); }
-        void setTau(float tau) { _tau = tau; rebuild(); }
+        // like the reference (filter.h:117-127) the setters only change scalars: legal while the worker is in run()
+        void setSampleRate(float sampleRate) { _sampleRate = sampleRate; if (h) { qdsp_deemp_set_params(h, _sampleRate, _tau); } }
+        void setTau(float tau) { _tau = tau; if (h) { qdsp_deemp_set_params(h, _sampleRate, _tau); } }
         int run() override {
             const int count = _in->readDevice(cuStream);
             if (count < 0) { return -1; }
@@ -98,11 +99,9 @@ namespace dsp {
         stream<stereo_t> out;
 
     private:
-        void rebuild() {
-            float l = 0, r = 0;
-            if (h) { qdsp_deemp_get_state(h, &l, &r); qdsp_deemp_destroy(h); }
+        void rebuild() {   // init() only: no worker thread exists yet
+            if (h) { qdsp_deemp_set_params(h, _sampleRate, _tau); return; }
             h = qdsp_deemp_create(_sampleRate, _tau);
-            qdsp_deemp_set_state(h, l, r);
         }
         float _sampleRate = 48000.0f, _tau = 50e-6f;
         stream<stereo_t>* _in = nullptr;

@@ -79,12 +79,12 @@ namespace dsp {
         void setSampleRate(float sampleRate) {
             std::lock_guard<std::mutex> lck(generic_block<AGC>::ctrlMtx);
             _sampleRate = sampleRate;
-            rebuild();
+            if (h) { qdsp_agc_set_params(h, _fallRate, _sampleRate); }   // scalar only (processing.h:101-106): state survives
         }
         void setFallRate(float fallRate) {
             std::lock_guard<std::mutex> lck(generic_block<AGC>::ctrlMtx);
             _fallRate = fallRate;
-            rebuild();
+            if (h) { qdsp_agc_set_params(h, _fallRate, _sampleRate); }
         }
         int run() override {
             const int count = _in->readDevice(cuStream);
@@ -101,11 +101,9 @@ namespace dsp {
         stream<float> out;
 
     private:
-        void rebuild() {
-            float level = 0.0f;
-            if (h) { qdsp_agc_get_state(h, &level); qdsp_agc_destroy(h); }
+        void rebuild() {   // init() only: no worker thread exists yet
+            if (h) { qdsp_agc_set_params(h, _fallRate, _sampleRate); return; }
             h = qdsp_agc_create(_fallRate, _sampleRate);
-            qdsp_agc_set_state(h, level);
         }
         float _fallRate = 0, _sampleRate = 1;
         stream<float>* _in = nullptr;
@@ -169,9 +167,10 @@ namespace dsp {
             generic_block<ComplexAGC>::registerOutput(&out);
         }
         void setInput(stream<complex_t>* in) { generic_block<ComplexAGC>::rebindInput(_in, in); }
-        void setSetPoint(float setPoint) { _setPoint = setPoint; rebuild(); }
-        void setMaxGain(float maxGain) { _maxGain = maxGain; rebuild(); }
-        void setRate(float rate) { _rate = rate; rebuild(); }
+        // like the reference (processing.h:258-269) the setters only change scalars: legal while the worker is in run()
+        void setSetPoint(float setPoint) { _setPoint = setPoint; if (h) { qdsp_cagc_set_params(h, _setPoint, _maxGain, _rate); } }
+        void setMaxGain(float maxGain) { _maxGain = maxGain; if (h) { qdsp_cagc_set_params(h, _setPoint, _maxGain, _rate); } }
+        void setRate(float rate) { _rate = rate; if (h) { qdsp_cagc_set_params(h, _setPoint, _maxGain, _rate); } }
         int run() override {
             const int count = _in->readDevice(cuStream);
             if (count < 0) { return -1; }
@@ -186,11 +185,9 @@ namespace dsp {
         stream<complex_t> out;
 
     private:
-        void rebuild() {
-            float gain = 1.0f;
-            if (h) { qdsp_cagc_get_state(h, &gain); qdsp_cagc_destroy(h); }
+        void rebuild() {   // init() only: no worker thread exists yet
+            if (h) { qdsp_cagc_set_params(h, _setPoint, _maxGain, _rate); return; }
             h = qdsp_cagc_create(_setPoint, _maxGain, _rate);
-            qdsp_cagc_set_state(h, gain);
         }
         float _setPoint = 1.0f, _maxGain = 65535.0f, _rate = 1e-3f;
         stream<complex_t>* _in = nullptr;

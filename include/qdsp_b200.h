@@ -48,6 +48,12 @@ int qdsp_copy_d2h(void* dst_host, const void* src_dev, size_t bytes, qdsp_stream
 int qdsp_copy_d2d(void* dst_dev, const void* src_dev, size_t bytes, qdsp_stream_t s);
 int qdsp_copy_peer(void* dst_dev, int dst_device, const void* src_dev, int src_device, size_t bytes, qdsp_stream_t s);
 int qdsp_enable_peer_access(int device, int peer);
+/* cross-process peer memory (one process per GPU): export a qdsp_malloc_device allocation as a 64-byte handle, map a
+ * peer process's handle into this process (reads / writes then travel over NVLink P2P), unmap it */
+#define QDSP_IPC_HANDLE_BYTES 64
+int qdsp_ipc_export(const void* dev_ptr, void* handle_out);
+void* qdsp_ipc_open(const void* handle);
+int qdsp_ipc_close(void* mapped);
 qdsp_stream_t qdsp_stream_create(void);
 void qdsp_stream_destroy(qdsp_stream_t s);
 int qdsp_stream_sync(qdsp_stream_t s);
@@ -86,6 +92,11 @@ int qdsp_fir_set_history(qdsp_fir* h, const void* hist_host);
 /* time-sharding halo: adopt the previous shard's last (tapCount-1) elements, read from a device
  * pointer that may live on a peer GPU (NVLink P2P); replaces the memmove at filter.h:71 */
 int qdsp_fir_import_tail(qdsp_fir* h, const void* tail_dev, int src_device, qdsp_stream_t s);
+/* the same without the copy: this ONE call reads its (tapCount-1)-element history straight from `halo_dev` -- any
+ * device-accessible pointer, e.g. the previous time shard's tail on a peer GPU mapped with qdsp_ipc_open (the kernel
+ * loads go over NVLink); NULL = zeros. The handle's own history then continues from this call's input (filter.h:71). */
+long long qdsp_fir_process_halo(qdsp_fir* h, const void* halo_dev, const void* in_dev, void* out_dev, long long count,
+                                qdsp_stream_t s);
 int qdsp_fir_reset(qdsp_fir* h);
 /* force a kernel variant: 0 = auto, 1 = generic, 2 = register-blocked sm_100a kernel */
 int qdsp_fir_set_variant(qdsp_fir* h, int variant);
@@ -166,6 +177,15 @@ int qdsp_vfofm_reset(qdsp_vfofm* h);
 int qdsp_vfofm_set_variant(qdsp_vfofm* h, int variant);
 /* time-sharding: start this shard at absolute stream sample `start` (NCO phase in closed form),
  * history/demod state imported from the previous shard */
+/* DEBUG replay of the reference's recursive float32 NCO (attribution of its drift, DESIGN.md "NCO"): the translator is
+ * evaluated run by run of 512 samples from `ckpt_host` -- the phase state volk_32fc_s32fc_x2_rotator_32fc holds at the start
+ * of every 512-sample run of every run() call (processing.h:64; n_ckpt = sum over blocks of ceil(count_b / 512), computed
+ * by the caller, e.g. with the oracle's rotator) -- with the reference's float recursion inside a run: the mixed samples are
+ * bit-identical to the reference's. Unfused (translator, resampler, demodulator as three kernels); state (history of the
+ * MIXED stream, demodulator phase) is separate from the fused path's: do not interleave the two on one handle. */
+long long qdsp_vfofm_process_replay(qdsp_vfofm* h, const void* in_dev, float* audio_out_dev, void* iq_out_dev,
+                                    long long count, const int* blocks, int nblocks, int block_size,
+                                    const float* ckpt_host, long long n_ckpt, qdsp_stream_t s);
 int qdsp_vfofm_seek(qdsp_vfofm* h, long long start);
 int qdsp_vfofm_import_tail(qdsp_vfofm* h, const void* tail_dev, int src_device, qdsp_stream_t s);
 int qdsp_vfofm_history_len(qdsp_vfofm* h);
@@ -197,6 +217,7 @@ typedef struct qdsp_deemp qdsp_deemp;
 qdsp_deemp* qdsp_deemp_create(float sampleRate, float tau);
 void qdsp_deemp_destroy(qdsp_deemp* h);
 long long qdsp_deemp_process(qdsp_deemp* h, const void* in_dev, void* out_dev, long long count, qdsp_stream_t s);
+int qdsp_deemp_set_params(qdsp_deemp* h, float sampleRate, float tau);       /* setSampleRate / setTau, filter.h:117-127: scalars only, state survives */
 int qdsp_deemp_get_state(qdsp_deemp* h, float* lastL, float* lastR);
 int qdsp_deemp_set_state(qdsp_deemp* h, float lastL, float lastR);
 
@@ -206,6 +227,7 @@ qdsp_agc* qdsp_agc_create(float fallRate, float sampleRate);
 void qdsp_agc_destroy(qdsp_agc* h);
 long long qdsp_agc_process(qdsp_agc* h, const float* in_dev, float* out_dev, long long count, const int* blocks,
                            int nblocks, int block_size, qdsp_stream_t s);
+int qdsp_agc_set_params(qdsp_agc* h, float fallRate, float sampleRate);      /* processing.h:101-113 */
 int qdsp_agc_get_state(qdsp_agc* h, float* level);
 int qdsp_agc_set_state(qdsp_agc* h, float level);
 
@@ -214,6 +236,7 @@ typedef struct qdsp_cagc qdsp_cagc;
 qdsp_cagc* qdsp_cagc_create(float setPoint, float maxGain, float rate);
 void qdsp_cagc_destroy(qdsp_cagc* h);
 long long qdsp_cagc_process(qdsp_cagc* h, const void* in_dev, void* out_dev, long long count, qdsp_stream_t s);
+int qdsp_cagc_set_params(qdsp_cagc* h, float setPoint, float maxGain, float rate); /* processing.h:258-269 */
 int qdsp_cagc_get_state(qdsp_cagc* h, float* gain);
 int qdsp_cagc_set_state(qdsp_cagc* h, float gain);
 

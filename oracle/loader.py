@@ -15,6 +15,8 @@ import os
 import subprocess
 from functools import lru_cache
 
+import math
+
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -509,6 +511,12 @@ class Port:
         L.port_vfo_design.restype = _i
         L.port_vfo_fm.argtypes = [_f, _f, _f, _f, _f, _i, _fp, _ip, _i, _fp, _ip, _fp]
         L.port_vfo_fm.restype = _ll
+        L.port_vfo_fm_window.argtypes = [_f, _f, _f, _f, _f, C.c_double, _fp, _ip, _i, _fp, _ip, _fp]
+        L.port_vfo_fm_window.restype = _ll
+        L.port_xlator_theta.argtypes = [_f, _f]
+        L.port_xlator_theta.restype = C.c_double
+        L.port_rotator_checkpoints.argtypes = [_f, _f, _fp, _fp, _ip, _i, _fp]
+        L.port_rotator_checkpoints.restype = _ll
         L.port_deemp.argtypes = [_f, _f, _fp, _ll, _fp, _fp, _fp]
         L.port_agc.argtypes = [_f, _f, _fp, _ip, _i, _fp, _fp]
         L.port_complex_agc.argtypes = [_f, _f, _f, _fp, _ll, _fp, _fp]
@@ -674,6 +682,36 @@ class Port:
         if want_iq:
             return a[:n].copy(), oc, iq[:n].copy()
         return a[:n].copy(), oc
+
+    def vfo_fm_window(self, offset, in_sr, out_sr, bw, dev, x, block, abs_start):
+        """The f64-NCO chain over a window x = stream[abs_start : abs_start + len(x)] (resampler from zero history:
+        discard the first ceil(T/D)+1 outputs). Returns (audio, out_counts, iq)."""
+        x, px = self._cin(x)
+        b = as_blocks(len(x), block)
+        i, d = self.rates_to_ratio(in_sr, out_sr)
+        cap = len(x) * i // d + len(b) + 16
+        a = np.empty(cap, np.float32)
+        iq = np.empty(cap, np.complex64)
+        oc = np.zeros(len(b), np.int32)
+        theta = self.lib.port_xlator_theta(in_sr, -offset)
+        start = math.fmod(theta * float(abs_start), 2.0 * math.pi) if abs_start < (1 << 50) else 0.0
+        # theta * abs_start in float64 loses ~1e-16 * abs_start rad: split the product to keep it exact to ~1e-12
+        hi, lo = divmod(int(abs_start), 1 << 20)
+        start = math.fmod(math.fmod(theta * float(1 << 20), 2.0 * math.pi) * hi, 2.0 * math.pi) + theta * lo
+        n = self.lib.port_vfo_fm_window(offset, in_sr, out_sr, bw, dev, start, px, _iptr(b), len(b), _fptr(a), _iptr(oc),
+                                        _fptr(iq.view(np.float32)))
+        return a[:n].copy(), oc, iq[:n].copy()
+
+    def rotator_checkpoints(self, inc: complex, block_sizes, phase: complex = 1 + 0j):
+        """Phase state of the float32 recursive rotator at the start of every 512-sample run of every call."""
+        b = np.ascontiguousarray(block_sizes, dtype=np.int32)
+        total = int(sum((int(c) + 511) // 512 for c in b))
+        ck = np.empty(max(total, 1) * 2, np.float32)
+        pr, pi = _f(np.float32(phase.real)), _f(np.float32(phase.imag))
+        k = self.lib.port_rotator_checkpoints(np.float32(inc.real), np.float32(inc.imag), C.byref(pr), C.byref(pi),
+                                              _iptr(b), len(b), _fptr(ck))
+        assert k == total
+        return ck[: 2 * total].view(np.complex64).copy(), complex(pr.value, pi.value)
 
     def deemp(self, fs, tau, x):
         x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, 2)

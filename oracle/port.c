@@ -412,6 +412,80 @@ long long port_vfo_fm(float offset, float inSR, float outSR, float bandWidth, fl
     return m;
 }
 
+/* Same composition over a WINDOW of a longer stream (bench / full-size parity checks): the drift-free rotator starts at
+ * angle start_ang (= theta * absolute index of x[0], reduced by the caller), the resampler from zero history. Outputs whose
+ * window reaches before x[0] (the first ceil(T/D) + 1) are start-up and must be discarded by the caller. */
+long long port_vfo_fm_window(float offset, float inSR, float outSR, float bandWidth, float deviation, double start_ang,
+                             const cf32* x, const int* blocks, int nblocks, float* audio, int* out_counts, cf32* iq_out) {
+    int I, D;
+    int T = port_vfo_design(inSR, outSR, bandWidth, NULL, 0, &I, &D);
+    float* taps = (float*)malloc((size_t)T * sizeof(float));
+    port_vfo_design(inSR, outSR, bandWidth, taps, T, &I, &D);
+    float inc_re, inc_im;
+    port_xlator_phase_delta(inSR, -offset, &inc_re, &inc_im);
+    long long n = 0;
+    for (int b = 0; b < nblocks; b++) n += blocks[b];
+    cf32* mixed = (cf32*)malloc((size_t)(n ? n : 1) * sizeof(cf32));
+    double ang = start_ang;
+    port_rotator_f64(x, mixed, inc_re, inc_im, &ang, n);
+    long long cap = (long long)((double)n * I / D) + nblocks + 16;
+    cf32* iq = iq_out ? iq_out : (cf32*)malloc((size_t)cap * sizeof(cf32));
+    long long m = port_resamp_cf32(taps, T, I, D, mixed, blocks, nblocks, iq, out_counts);
+    float st = 0.0f;
+    if (audio) port_fm_demod(iq, m, port_fm_phasor_speed(outSR, deviation), &st, audio);
+    if (!iq_out) free(iq);
+    free(mixed);
+    free(taps);
+    return m;
+}
+/* theta of the float-rounded phase increment (what the f64 rotator and the CUDA closed-form NCO both use) */
+double port_xlator_theta(float sampleRate, float freq) {
+    float re, im;
+    port_xlator_phase_delta(sampleRate, freq, &re, &im);
+    return atan2((double)im, (double)re);
+}
+
+/* The rotator's phase STATE at the start of every 512-sample run of every call (block), i.e. what
+ * volk_32fc_s32fc_x2_rotator_32fc_generic holds right after each renormalisation (and at the start of each call). The
+ * sequence does not depend on the samples. ckpt[2*k], ckpt[2*k+1] = (re, im) for run k; runs are numbered block by
+ * block, ceil(count_b / 512) per block. Returns the number of runs; *phase_re/_im carry the state across calls. */
+long long port_rotator_checkpoints(float inc_re, float inc_im, float* phase_re, float* phase_im, const int* blocks,
+                                   int nblocks, float* ckpt) {
+    float pr = *phase_re, pi = *phase_im;
+    long long k = 0;
+    for (int b = 0; b < nblocks; b++) {
+        int count = blocks[b];
+        for (int seg = 0; seg < count / 512; seg++) {
+            if (ckpt) { ckpt[2 * k] = pr; ckpt[2 * k + 1] = pi; }
+            k++;
+            for (int j = 0; j < 512; j++) {
+                float nr = pr * inc_re - pi * inc_im, ni = pr * inc_im + pi * inc_re;
+                pr = nr;
+                pi = ni;
+            }
+            float h = hypotf(pr, pi);
+            pr /= h;
+            pi /= h;
+        }
+        int rem = count % 512;
+        if (rem) {
+            if (ckpt) { ckpt[2 * k] = pr; ckpt[2 * k + 1] = pi; }
+            k++;
+            for (int j = 0; j < rem; j++) {
+                float nr = pr * inc_re - pi * inc_im, ni = pr * inc_im + pi * inc_re;
+                pr = nr;
+                pi = ni;
+            }
+            float h = hypotf(pr, pi);
+            pr /= h;
+            pi /= h;
+        }
+    }
+    *phase_re = pr;
+    *phase_im = pi;
+    return k;
+}
+
 void port_agc(float fallRate, float sampleRate, const float* x, const int* blocks, int nblocks, float* y, float* level_state);
 
 /* StereoFMDemod::run, src/dsp/demodulator.h:255-277, with its sub-blocks composed as init() wires them

@@ -268,6 +268,10 @@ class FIR(_Block):
     def import_tail(self, tail_ptr, src_device=-1, stream=None):
         check(_L().qdsp_fir_import_tail(self.h, tail_ptr, src_device, stream), "qdsp_fir_import_tail")
 
+    def process_halo_device(self, halo_ptr, in_ptr, out_ptr, n, stream=None) -> int:
+        """One call whose (tapCount-1)-sample history is read straight from `halo_ptr` (may be peer-mapped); None = zeros."""
+        return int(check(_L().qdsp_fir_process_halo(self.h, halo_ptr, in_ptr, out_ptr, int(n), stream), "qdsp_fir_process_halo"))
+
     def set_history(self, hist: np.ndarray):
         hist = np.ascontiguousarray(hist, self.in_dtype)
         assert len(hist) == self.history_len()
@@ -516,6 +520,45 @@ class VFOFM(_Block):
         b, nb, bs = _blocks_arg(n, block)
         return int(check(_L().qdsp_vfofm_out_count(self.h, n, _iptr(b), nb, bs)))
 
+    def process_replay(self, x, block, ckpt: np.ndarray, want_iq=False):
+        """DEBUG: the chain with the reference's recursive float32 NCO replayed from per-512-sample phase checkpoints
+        (`ckpt`: complex64, one per 512-sample run of every run() block). Returns audio (and the resampled IQ)."""
+        x = np.ascontiguousarray(x, np.complex64)
+        n = len(x)
+        ck = np.ascontiguousarray(ckpt, np.complex64).view(np.float32)
+        din = DevBuf.from_numpy(x)
+        cap = self._out_capacity(n, block)
+        dout = DevBuf(max(cap, 1) * 4)
+        diq = DevBuf(max(cap, 1) * 8) if want_iq else None
+        b, nb, bs = _blocks_arg(n, block)
+        m = int(check(_L().qdsp_vfofm_process_replay(self.h, din.ptr, dout.ptr, diq.ptr if diq else None, n, _iptr(b), nb, bs,
+                                                     _fptr(ck), len(ck) // 2, None), "qdsp_vfofm_process_replay"))
+        y = dout.to_numpy(np.float32, m)
+        iq = diq.to_numpy(np.complex64, m) if diq else None
+        din.free()
+        dout.free()
+        if diq:
+            diq.free()
+        return (y, iq) if want_iq else y
+
+    def process_host(self, x: np.ndarray, block: int) -> np.ndarray:
+        """The host-buffer entry point (qdsp_vfofm_process_host): pinned host in / out, chunked H2D | kernel | D2H."""
+        x = np.ascontiguousarray(x, np.complex64)
+        n = len(x)
+        L = _L()
+        hin = L.qdsp_malloc_pinned(max(n, 1) * 8)
+        cap = self._out_capacity(n, block)
+        hout = L.qdsp_malloc_pinned(max(cap, 1) * 4)
+        try:
+            C.memmove(hin, x.ctypes.data, n * 8)
+            m = int(check(L.qdsp_vfofm_process_host(self.h, hin, hout, n, int(block), None), "qdsp_vfofm_process_host"))
+            y = np.empty(m, np.float32)
+            C.memmove(y.ctypes.data, hout, m * 4)
+        finally:
+            L.qdsp_free_pinned(hin)
+            L.qdsp_free_pinned(hout)
+        return y
+
     def _out_capacity(self, n, block):
         return (n * self._interp) // self._decim + 16
 
@@ -539,8 +582,8 @@ class VFOFM(_Block):
         self.last_iq = diq.to_numpy(np.complex64, m)
         return dout.to_numpy(np.float32, m)
 
-    def process_host(self, x: np.ndarray, out: np.ndarray, block_size: int, stream=None) -> int:
-        """End-to-end call with HOST buffers (pinned for real overlap): chunked H2D/compute/D2H inside."""
+    def process_host_into(self, x: np.ndarray, out: np.ndarray, block_size: int, stream=None) -> int:
+        """End-to-end call with caller-owned HOST buffers (pinned for real overlap): chunked H2D/compute/D2H inside."""
         return int(check(_L().qdsp_vfofm_process_host(self.h, x.ctypes.data, out.ctypes.data, len(x), int(block_size),
                                                       stream), "qdsp_vfofm_process_host"))
 

@@ -167,6 +167,28 @@ long long qdsp_fir_process(qdsp_fir* h, const void* in_dev, void* out_dev, long 
     if (h->hist.advance(in_dev, count, s) != 0) return -1;
     return count;
 }
+long long qdsp_fir_process_halo(qdsp_fir* h, const void* halo_dev, const void* in_dev, void* out_dev, long long count,
+                                qdsp_stream_t s_) {
+    cudaStream_t s = as_stream(s_);
+    if (count < 0) return -1;
+    if (count == 0) return 0;
+    if (!h->plan) {
+        set_last_error("fir_process_halo: cf32 filters only");
+        return -1;
+    }
+    // halo_dev == NULL: zero history (H = 0: every read before sample 0 returns zero)
+    if (launch_fir_dense(h->plan, (const float2*)halo_dev, halo_dev ? h->hist.H : 0, (const float2*)in_dev, count, 1,
+                         (float2*)out_dev, s) != 0)
+        return -1;
+    if (count >= h->hist.H) {
+        if (h->hist.advance(in_dev, count, s) != 0) return -1;
+    } else {   // short call: the new tail still contains halo samples
+        if (halo_dev) QDSP_CUDA_OK(cudaMemcpyAsync(h->hist.buf[h->hist.cur], halo_dev, (size_t)h->hist.H * h->hist.elem, cudaMemcpyDefault, s));
+        else QDSP_CUDA_OK(cudaMemsetAsync(h->hist.buf[h->hist.cur], 0, (size_t)h->hist.H * h->hist.elem, s));
+        if (h->hist.advance(in_dev, count, s) != 0) return -1;
+    }
+    return count;
+}
 int qdsp_fir_history_len(qdsp_fir* h) { return h->hist.H; }
 int qdsp_fir_get_history(qdsp_fir* h, void* hist_host) {
     QDSP_CUDA_OK(cudaDeviceSynchronize());
@@ -456,6 +478,13 @@ struct qdsp_channelizer {
     cudaEvent_t ev_done[2] = {nullptr, nullptr};
     cudaStream_t copy_stream = nullptr;
     size_t stage_samples = 0;
+    // debug replay of the reference's recursive NCO (process_replay): its own state
+    History hist_mixed;          // tail of the MIXED stream (resampling.h:129)
+    DevState demod_replay;       // [2] ping-pong demodulator phase
+    int cur_replay = 0;
+    Scratch replay_scratch;      // mixed stream | resampled IQ | run table | checkpoints
+    Partition part_replay;
+    DecimPlan* plan_replay = nullptr;
     // bench hook: events around the dominant kernel
     bool timing = false;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;          // the current launch's pair (= ring[ring_pos])
@@ -548,7 +577,9 @@ struct qdsp_channelizer {
         if (nco_dev) cudaFree(nco_dev);
         if (phases_dev) cudaFree(phases_dev);
         if (plan) decim_plan_destroy(plan);
+        if (plan_replay) decim_plan_destroy(plan_replay);
         hist.release();
+        hist_mixed.release();
         for (int i = 0; i < 2; i++) {
             if (stage_in[i]) cudaFree(stage_in[i]);
             if (stage_out[i]) cudaFree(stage_out[i]);
@@ -666,6 +697,73 @@ long long qdsp_vfofm_process_host(qdsp_vfofm* h, const void* in_host, float* aud
     QDSP_CUDA_OK(cudaStreamSynchronize(s));
     for (int i = 0; i < 2; i++) cudaEventDestroy(ev_h2d[i]);
     return produced;
+}
+long long qdsp_vfofm_process_replay(qdsp_vfofm* h, const void* in_dev, float* audio_out_dev, void* iq_out_dev,
+                                    long long count, const int* blocks, int nblocks, int block_size,
+                                    const float* ckpt_host, long long n_ckpt, qdsp_stream_t s_) {
+    qdsp_channelizer& c = h->c;
+    cudaStream_t s = as_stream(s_);
+    if (c.nch != 1 || !ckpt_host) {
+        set_last_error("vfofm_process_replay: bad arguments");
+        return -1;
+    }
+    if (c.part_replay.build(count, blocks, nblocks, block_size, c.interp, c.decim, s) != 0) return -1;
+    if (count == 0) return 0;
+    const Partition& part = c.part_replay;
+    const int nb = part.view.nblocks;
+    std::vector<long long> run0((size_t)nb + 1, 0);
+    for (int b = 0; b < nb; b++) {
+        long long cnt;
+        if (blocks) cnt = part.host[b].count;
+        else {
+            const long long st = (long long)b * part.view.block_size;
+            cnt = count - st < part.view.block_size ? count - st : part.view.block_size;
+        }
+        run0[b + 1] = run0[b] + (cnt + 511) / 512;
+    }
+    if (run0[nb] != n_ckpt) {
+        set_last_error("vfofm_process_replay: %lld checkpoints given, the partition has %lld runs", n_ckpt, run0[nb]);
+        return -1;
+    }
+    if (!c.hist_mixed.buf[0]) {
+        if (c.hist_mixed.init(c.tpp, 8) != 0) return -1;
+        const float z[2] = {0.f, 0.f};
+        if (c.demod_replay.init(2, z) != 0) return -1;
+    }
+    const size_t n_out_cap = (size_t)part.total_out + 64;
+    const size_t off_iq = ((size_t)count * 8 + 255) / 256 * 256;
+    const size_t off_run = off_iq + (n_out_cap * 8 + 255) / 256 * 256;
+    const size_t off_ck = off_run + (((size_t)nb + 1) * 8 + 255) / 256 * 256;
+    if (c.replay_scratch.reserve(off_ck + (size_t)n_ckpt * 8 + 256) != 0) return -1;
+    char* base = (char*)c.replay_scratch.p;
+    float2* mixed = (float2*)base;
+    float2* iq = iq_out_dev ? (float2*)iq_out_dev : (float2*)(base + off_iq);
+    long long* run0_dev = (long long*)(base + off_run);
+    float2* ck_dev = (float2*)(base + off_ck);
+    QDSP_CUDA_OK(cudaMemcpyAsync(run0_dev, run0.data(), ((size_t)nb + 1) * 8, cudaMemcpyHostToDevice, s));
+    QDSP_CUDA_OK(cudaMemcpyAsync(ck_dev, ckpt_host, (size_t)n_ckpt * 8, cudaMemcpyHostToDevice, s));
+    QDSP_CUDA_OK(cudaStreamSynchronize(s));   // run0 / ckpt_host may be released by the caller after return
+    if (launch_xlator_replay((const float2*)in_dev, mixed, part, run0_dev, ck_dev, make_float2(c.nco[0].inc_re, c.nco[0].inc_im),
+                             n_ckpt, s) != 0)
+        return -1;
+    int rc;
+    if (c.plan && c.variant != 1) {
+        if (!c.plan_replay) c.plan_replay = decim_plan_create(c.taps.data(), c.T, c.decim);
+        rc = launch_decim(c.plan_replay, (const float2*)c.hist_mixed.ptr(), c.hist_mixed.H, mixed, part, 0, nullptr, 0, 1, 0.0f,
+                          nullptr, nullptr, iq, nullptr, 0, s);
+    } else {
+        rc = launch_generic_resamp<float2>((const float2*)c.hist_mixed.ptr(), c.hist_mixed.H, mixed, c.phases_dev, c.tpp, 0,
+                                           part, iq, s);
+    }
+    if (rc != 0) return -1;
+    if (c.hist_mixed.advance(mixed, count, s) != 0) return -1;
+    if (part.total_out > 0) {
+        if (launch_fmdemod(iq, audio_out_dev, part.total_out, c.phasor_speed, c.demod_replay.p + c.cur_replay,
+                           c.demod_replay.p + (c.cur_replay ^ 1), 0, s) != 0)
+            return -1;
+        c.cur_replay ^= 1;
+    }
+    return part.total_out;
 }
 int qdsp_vfofm_reset(qdsp_vfofm* h) {
     qdsp_channelizer& c = h->c;
@@ -835,6 +933,13 @@ long long qdsp_deemp_process(qdsp_deemp* h, const void* in_dev, void* out_dev, l
         return -1;
     return count;
 }
+int qdsp_deemp_set_params(qdsp_deemp* h, float sampleRate, float tau) {
+    // like the reference's setters (filter.h:117-127) only scalars change: handle and device state survive, the
+    // next process() call picks the new alpha up
+    const float dt = 1.0f / sampleRate;
+    h->alpha = dt / (tau + dt);
+    return 0;
+}
 int qdsp_deemp_get_state(qdsp_deemp* h, float* lastL, float* lastR) {
     float v[2];
     if (h->st.get(v, 2) != 0) return -1;
@@ -871,6 +976,10 @@ long long qdsp_agc_process(qdsp_agc* h, const float* in_dev, float* out_dev, lon
     if (launch_agc(in_dev, out_dev, h->part, h->corrected, h->st.p, bm, bm + 32 * (size_t)nb, s) != 0) return -1;
     return count;
 }
+int qdsp_agc_set_params(qdsp_agc* h, float fallRate, float sampleRate) {   // processing.h:101-113
+    h->corrected = fallRate / sampleRate;
+    return 0;
+}
 int qdsp_agc_get_state(qdsp_agc* h, float* level) { return h->st.get(level, 1); }
 int qdsp_agc_set_state(qdsp_agc* h, float level) { return h->st.set(&level, 1); }
 
@@ -896,6 +1005,12 @@ long long qdsp_cagc_process(qdsp_cagc* h, const void* in_dev, void* out_dev, lon
                     h->scratch.p, h->scratch.cap, as_stream(s)) != 0)
         return -1;
     return count;
+}
+int qdsp_cagc_set_params(qdsp_cagc* h, float setPoint, float maxGain, float rate) {   // processing.h:258-269
+    h->set_point = setPoint;
+    h->max_gain = maxGain;
+    h->rate = rate;
+    return 0;
 }
 int qdsp_cagc_get_state(qdsp_cagc* h, float* gain) { return h->st.get(gain, 1); }
 int qdsp_cagc_set_state(qdsp_cagc* h, float gain) { return h->st.set(&gain, 1); }
@@ -965,6 +1080,10 @@ long long qdsp_costas_process(qdsp_costas* h, const void* in_dev, void* out_dev,
 int qdsp_costas_get_state(qdsp_costas* h, float state[4]) { return h->st.get(state, 4); }
 int qdsp_costas_set_state(qdsp_costas* h, const float state[4]) { return h->st.set(state, 4); }
 int qdsp_costas_set_chunking(qdsp_costas* h, int chunk, int warmup) {
+    if (chunk < 16 || warmup < 0 || (chunk % 16) != 0 || (warmup % 16) != 0) {
+        set_last_error("costas_set_chunking: chunk must be a positive multiple of 16, warmup a non-negative multiple of 16");
+        return -1;
+    }
     h->chunk = chunk;
     h->warmup = warmup;
     return 0;

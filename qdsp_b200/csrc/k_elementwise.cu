@@ -52,9 +52,54 @@ __global__ void __launch_bounds__(256) xlator_kernel(const float2* __restrict__ 
             out[n] = cmul_exact(in[n], phasor_from_turns(phase0 + step * (uint64_t)n));
     }
 }
+// pointers that are only 8-byte aligned (a sub-window of a buffer, an odd time-shard start): one sample per thread
+__global__ void __launch_bounds__(256) xlator_scalar_kernel(const float2* __restrict__ in, float2* __restrict__ out,
+                                                           long long count, uint64_t phase0, uint64_t step) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x; n < count; n += stride)
+        out[n] = cmul_exact(ldg_stream64(in + n), phasor_from_turns(phase0 + step * (uint64_t)n));
+}
+// Debug replay of the reference's recursive float32 rotator (volk_32fc_s32fc_x2_rotator_32fc_generic): one thread
+// per 512-sample run starts from the host-supplied phase state of that run and repeats the float recursion
+// out = in * phase; phase *= inc with every product and sum rounded separately -- bit-identical to the reference.
+__global__ void __launch_bounds__(128) xlator_replay_kernel(const float2* __restrict__ in, float2* __restrict__ out,
+                                                           const PartitionDev part, const long long* __restrict__ run0,
+                                                           const float2* __restrict__ ckpt, float2 inc, long long nruns) {
+    const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (r >= nruns) return;
+    // block of run r: largest b with run0[b] <= r
+    int lo = 0, hi = part.nblocks - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (run0[mid] <= r) lo = mid;
+        else hi = mid - 1;
+    }
+    const BlkInfo bi = part.get(lo);
+    const long long first = bi.in_start + (r - run0[lo]) * 512;
+    const long long end = bi.in_start + bi.count;
+    const int n = (int)(end - first < 512 ? end - first : 512);
+    float2 p = ckpt[r];
+    for (int j = 0; j < n; j++) {
+        out[first + j] = cmul_exact(in[first + j], p);
+        p = cmul_exact(p, inc);
+    }
+}
+int launch_xlator_replay(const float2* in, float2* out, const Partition& part, const long long* run0_dev,
+                         const float2* ckpt_dev, float2 inc, long long nruns, cudaStream_t s) {
+    if (nruns <= 0) return 0;
+    xlator_replay_kernel<<<(unsigned)((nruns + 127) / 128), 128, 0, s>>>(in, out, part.view, run0_dev, ckpt_dev, inc, nruns);
+    QDSP_LAUNCH_OK();
+    return 0;
+}
+
 int launch_xlator(const float2* in, float2* out, long long count, uint64_t phase0, uint64_t step, float2 inc1,
                   float2 inc2, float2 inc3, cudaStream_t s) {
     if (count <= 0) return 0;
+    if (((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) != 0) {
+        xlator_scalar_kernel<<<stream_grid(count, 256, 8), 256, 0, s>>>(in, out, count, phase0, step);
+        QDSP_LAUNCH_OK();
+        return 0;
+    }
     xlator_kernel<<<stream_grid(count / 4 + 1, 256, 8), 256, 0, s>>>(in, out, count, phase0, step, inc1, inc2, inc3);
     QDSP_LAUNCH_OK();
     return 0;
@@ -102,10 +147,23 @@ __global__ void __launch_bounds__(256) power_decim_kernel(const float4* __restri
         out[m] = make_float2(__fmul_rn(__fadd_rn(v.x, v.z), 0.5f), __fmul_rn(__fadd_rn(v.y, v.w), 0.5f));
     }
 }
+__global__ void __launch_bounds__(256) power_decim_scalar_kernel(const float2* __restrict__ in, float2* __restrict__ out,
+                                                                long long n_out) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < n_out; m += stride) {
+        const float2 a = ldg_stream64(in + 2 * m), b = ldg_stream64(in + 2 * m + 1);
+        out[m] = make_float2(__fmul_rn(__fadd_rn(a.x, b.x), 0.5f), __fmul_rn(__fadd_rn(a.y, b.y), 0.5f));
+    }
+}
 int launch_power_decim(const float2* in, float2* out, long long n_out, int copy_only, cudaStream_t s) {
     if (n_out <= 0) return 0;
     if (copy_only) {
         QDSP_CUDA_OK(cudaMemcpyAsync(out, in, (size_t)n_out * sizeof(float2), cudaMemcpyDeviceToDevice, s));
+        return 0;
+    }
+    if ((reinterpret_cast<uintptr_t>(in) & 15) != 0) {   // 8-byte aligned input: no 128-bit loads
+        power_decim_scalar_kernel<<<stream_grid(n_out, 256, 8), 256, 0, s>>>(in, out, n_out);
+        QDSP_LAUNCH_OK();
         return 0;
     }
     power_decim_kernel<<<stream_grid(n_out, 256, 8), 256, 0, s>>>(reinterpret_cast<const float4*>(in), out, n_out);

@@ -37,7 +37,6 @@ __global__ void __launch_bounds__(32) decim_rowlane_kernel(const __grid_constant
     constexpr int LEAD = DEMOD ? 1 : 0;
     constexpr int P = D / 2;
     constexpr uint32_t STAGE_BYTES = 32u * D * 8u;
-    constexpr int RESEED = 4;
     static_assert((P & 1) == 1, "row pitch must be an odd number of 16-byte units (conflict-free 128-bit loads)");
     static_assert(Q >= 2 && Q <= 24, "Q");
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -121,8 +120,6 @@ __global__ void __launch_bounds__(32) decim_rowlane_kernel(const __grid_constant
 
     // ---- per-lane state -------------------------------------------------------------------------------
     float2 Pr = make_float2(1.f, 0.f);        // row phasor of this lane's current row
-    float2 w32 = make_float2(1.f, 0.f);       // e^{j theta 32 D}: one step down the rows
-    if (ROT) w32 = phasor_from_turns(nco_step * (uint64_t)(32 * D));
     float2 old = make_float2(0.f, 0.f);       // partial output of (previous step, this lane), lanes >= 32-(Q-1)
     float ang_saved = 0.f;
     const bool tail_lane = lane >= 32 - (Q - 1);
@@ -132,12 +129,11 @@ __global__ void __launch_bounds__(32) decim_rowlane_kernel(const __grid_constant
     for (int i = 0; i < nsteps; i++) {
         const int slot = i % NSTG;
         if (ROT) {
-            if (i % RESEED == 0) {
-                const long long n0 = row0 + (long long)(32 * i + lane) * D;
-                Pr = phasor_from_turns(nco_ph0 + nco_step * (uint64_t)n0);
-            } else {
-                Pr = cmul(Pr, w32);
-            }
+            // the row phasor is a pure function of the row's absolute sample index (closed form, no recurrence down the
+            // rows): an output's value does not depend on which tile / step / lane computes it, so any batching of the
+            // stream into process() calls (and the chunking of process_host) gives bit-identical audio
+            const long long n0 = row0 + (long long)(32 * i + lane) * D;
+            Pr = phasor_from_turns(nco_ph0 + nco_step * (uint64_t)n0);
         }
         mbar_wait(&mbar[slot], (uint32_t)((i / NSTG) & 1));
         const float4* xrow = reinterpret_cast<const float4*>(smem_raw + slot * STAGE_BYTES + lane * (D * 8));

@@ -25,6 +25,8 @@ int launch_generic_vfofm(const float2* hist, int H, const float2* in, const floa
 // ---- k_elementwise.cu ---------------------------------------------------------------------------
 int launch_xlator(const float2* in, float2* out, long long count, uint64_t phase0, uint64_t step, float2 inc1,
                   float2 inc2, float2 inc3, cudaStream_t s);
+int launch_xlator_replay(const float2* in, float2* out, const Partition& part, const long long* run0_dev,
+                         const float2* ckpt_dev, float2 inc, long long nruns, cudaStream_t s);
 int launch_fmdemod(const float2* in, void* out, long long count, float phasor_speed, const float* state_in,
                    float* state_out, int stereo, cudaStream_t s);
 int launch_stereo_matrix(const float* mpx, const float* pilot, float2* out, long long count, cudaStream_t s);

@@ -270,6 +270,29 @@ int qdsp_enable_peer_access(int device, int peer) {
     QDSP_CUDA_OK(e);
     return 0;
 }
+int qdsp_ipc_export(const void* dev_ptr, void* handle_out) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == QDSP_IPC_HANDLE_BYTES, "ipc handle size");
+    cudaIpcMemHandle_t hnd;
+    QDSP_CUDA_OK(cudaIpcGetMemHandle(&hnd, const_cast<void*>(dev_ptr)));
+    memcpy(handle_out, &hnd, sizeof(hnd));
+    return 0;
+}
+void* qdsp_ipc_open(const void* handle) {
+    cudaIpcMemHandle_t hnd;
+    memcpy(&hnd, handle, sizeof(hnd));
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_last_error("cudaIpcOpenMemHandle -> %s", cudaGetErrorString(e));
+        return nullptr;
+    }
+    return p;
+}
+int qdsp_ipc_close(void* mapped) {
+    if (mapped) QDSP_CUDA_OK(cudaIpcCloseMemHandle(mapped));
+    return 0;
+}
 qdsp_stream_t qdsp_stream_create(void) {
     cudaStream_t s = nullptr;
     cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);

@@ -38,6 +38,9 @@ SIGNATURES = {
     "qdsp_copy_d2d": (_i, [_vp, _vp, _sz, _vp]),
     "qdsp_copy_peer": (_i, [_vp, _i, _vp, _i, _sz, _vp]),
     "qdsp_enable_peer_access": (_i, [_i, _i]),
+    "qdsp_ipc_export": (_i, [_vp, _vp]),
+    "qdsp_ipc_open": (_vp, [_vp]),
+    "qdsp_ipc_close": (_i, [_vp]),
     "qdsp_stream_create": (_vp, []),
     "qdsp_stream_destroy": (None, [_vp]),
     "qdsp_stream_sync": (_i, [_vp]),
@@ -62,6 +65,7 @@ SIGNATURES = {
     "qdsp_fir_get_history": (_i, [_vp, _vp]),
     "qdsp_fir_set_history": (_i, [_vp, _vp]),
     "qdsp_fir_import_tail": (_i, [_vp, _vp, _i, _vp]),
+    "qdsp_fir_process_halo": (_ll, [_vp, _vp, _vp, _vp, _ll, _vp]),
     "qdsp_fir_reset": (_i, [_vp]),
     "qdsp_fir_set_variant": (_i, [_vp, _i]),
     "qdsp_resamp_create": (_vp, [_i, _fp, _i, _i, _i]),
@@ -102,6 +106,7 @@ SIGNATURES = {
     "qdsp_vfofm_out_count": (_ll, [_vp, _ll, _ip, _i, _i]),
     "qdsp_vfofm_process": (_ll, [_vp, _vp, _vp, _vp, _ll, _ip, _i, _i, _ip, _vp]),
     "qdsp_vfofm_process_host": (_ll, [_vp, _vp, _vp, _ll, _i, _vp]),
+    "qdsp_vfofm_process_replay": (_ll, [_vp, _vp, _vp, _vp, _ll, _ip, _i, _i, _fp, _ll, _vp]),
     "qdsp_vfofm_reset": (_i, [_vp]),
     "qdsp_vfofm_set_variant": (_i, [_vp, _i]),
     "qdsp_vfofm_seek": (_i, [_vp, _ll]),
@@ -120,16 +125,19 @@ SIGNATURES = {
     "qdsp_deemp_create": (_vp, [_f, _f]),
     "qdsp_deemp_destroy": (None, [_vp]),
     "qdsp_deemp_process": (_ll, [_vp, _vp, _vp, _ll, _vp]),
+    "qdsp_deemp_set_params": (_i, [_vp, _f, _f]),
     "qdsp_deemp_get_state": (_i, [_vp, _fp, _fp]),
     "qdsp_deemp_set_state": (_i, [_vp, _f, _f]),
     "qdsp_agc_create": (_vp, [_f, _f]),
     "qdsp_agc_destroy": (None, [_vp]),
     "qdsp_agc_process": (_ll, [_vp, _vp, _vp, _ll, _ip, _i, _i, _vp]),
+    "qdsp_agc_set_params": (_i, [_vp, _f, _f]),
     "qdsp_agc_get_state": (_i, [_vp, _fp]),
     "qdsp_agc_set_state": (_i, [_vp, _f]),
     "qdsp_cagc_create": (_vp, [_f, _f, _f]),
     "qdsp_cagc_destroy": (None, [_vp]),
     "qdsp_cagc_process": (_ll, [_vp, _vp, _vp, _ll, _vp]),
+    "qdsp_cagc_set_params": (_i, [_vp, _f, _f, _f]),
     "qdsp_cagc_get_state": (_i, [_vp, _fp]),
     "qdsp_cagc_set_state": (_i, [_vp, _f]),
     "qdsp_ffagc_create": (_vp, [_i]),

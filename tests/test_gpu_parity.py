@@ -44,8 +44,9 @@ def test_filtered_samples(name, variant, golden):
         P = loader.port()
         _, _, iq64 = P.vfo_fm(c["offset"], c["in_sr"], c["out_sr"], c["bw"], 5e3, x, c["block"], nco_f64=True, want_iq=True)
         assert rel_l2(y, iq64) <= IQ_TOL, rel_l2(y, iq64)
-        drift = rel_l2(g, iq64)
-        assert rel_l2(y, g) <= drift + IQ_TOL
+        # against the float32-rotator reference vector itself: 40 000 samples is short enough that its drift is small; the
+        # full-length attribution is tests/test_gpu_fullsize.py::test_nco_attribution_at_reference_block_size
+        assert rel_l2(y, g) <= 1e-4, rel_l2(y, g)
         return
     assert rel_l2(y[s:], g[s:]) <= IQ_TOL, rel_l2(y[s:], g[s:])
     assert rel_l2(y[s:], yo[s:]) <= IQ_TOL
