@@ -360,6 +360,12 @@ long long qdsp_sinesource_process(qdsp_sinesource* h, void* out_dev, long long c
 int qdsp_synth_uniform_cf32(void* out_dev, unsigned long long seed, long long start, long long count, qdsp_stream_t s);
 int qdsp_synth_fm_cf32(void* out_dev, long long start, long long count, long long fs, long long fc, long long fm,
                        double dev, double amp, double noise_amp, unsigned long long noise_seed, qdsp_stream_t s);
+/* config 4's wideband comb (nch FM carriers `spacing` Hz apart, fm = 300 + 10k Hz) and config 5's QPSK streams; float32
+ * evaluation of exact integer phase fractions -- test signals, the oracle consumes the generated samples themselves */
+int qdsp_synth_comb_cf32(void* out_dev, long long start, long long count, long long fs, int nch, long long spacing,
+                         double dev, double amp, double noise_amp, unsigned long long noise_seed, qdsp_stream_t s);
+int qdsp_synth_qpsk_cf32(void* out_dev, long long start, long long count, unsigned long long seed, int sps, double freq_off,
+                         double sigma, double am_depth, long long am_period, qdsp_stream_t s);
 
 /* ---- microbenchmarks used by bench.py to measure the FP32 roofline denominator -------------- */
 /* runs `iters` dependent-chain FMA iterations on every SM; returns achieved TFLOP/s (2 flop/FMA) */

@@ -1161,6 +1161,14 @@ int qdsp_synth_fm_cf32(void* out_dev, long long start, long long count, long lon
                        double dev, double amp, double noise_amp, unsigned long long noise_seed, qdsp_stream_t s) {
     return launch_synth_fm((float2*)out_dev, start, count, fs, fc, fm, dev, amp, noise_amp, noise_seed, as_stream(s));
 }
+int qdsp_synth_comb_cf32(void* out_dev, long long start, long long count, long long fs, int nch, long long spacing,
+                         double dev, double amp, double noise_amp, unsigned long long noise_seed, qdsp_stream_t s) {
+    return launch_synth_comb((float2*)out_dev, start, count, fs, nch, spacing, dev, amp, noise_amp, noise_seed, as_stream(s));
+}
+int qdsp_synth_qpsk_cf32(void* out_dev, long long start, long long count, unsigned long long seed, int sps, double freq_off,
+                         double sigma, double am_depth, long long am_period, qdsp_stream_t s) {
+    return launch_synth_qpsk((float2*)out_dev, start, count, seed, sps, freq_off, sigma, am_depth, am_period, as_stream(s));
+}
 double qdsp_measure_fp32_peak(int packed, int iters) { return run_fp32_peak(packed, iters); }
 
 }  // extern "C"

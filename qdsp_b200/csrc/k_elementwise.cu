@@ -247,6 +247,78 @@ int launch_synth_fm(float2* out, long long start, long long count, long long fs,
     return 0;
 }
 
+// BASELINE config 4 wideband input (qdsp_b200/synth.py cfg4_input): sum of nch FM carriers at (k-(nch-1)/2)*spacing,
+// fm = 300+10k Hz, dev 5 kHz, A = amp, + noise_amp * U(seed, n). Phases from exact integer fractions, evaluated in float32
+// (a synthetic test signal: the oracle consumes the very samples generated here, copied back).
+__global__ void __launch_bounds__(256) synth_comb_kernel(float2* __restrict__ out, long long start, long long count,
+                                                        long long fs, int nch, long long spacing, float dev, float amp,
+                                                        float noise_amp, unsigned long long noise_seed) {
+    const float two_pi = 6.283185307179586f;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += stride) {
+        const long long n = start + i;
+        float ar = 0.f, ai = 0.f;
+        for (int k = 0; k < nch; k++) {
+            // fc = (2k - (nch-1)) * spacing / 2 may be a half-integer multiple of spacing: work in units of fs * 2
+            const long long fc2 = (2ll * k - (nch - 1)) * spacing;          // 2 * fc
+            long long r = (((n % (2 * fs)) * (fc2 % (2 * fs))) % (2 * fs));
+            if (r < 0) r += 2 * fs;
+            const float pc = (float)((double)r / (double)(2 * fs));
+            const long long fm = 300 + 10 * k;
+            const float pm = (float)frac_ratio(n, fm, fs);
+            float sm, cm_;
+            sincosf(two_pi * pm, &sm, &cm_);
+            float sn, cs;
+            sincosf(two_pi * pc + (dev / (float)fm) * sm, &sn, &cs);
+            ar += cs;
+            ai += sn;
+        }
+        float2 v = make_float2(amp * ar, amp * ai);
+        if (noise_amp != 0.0f) {
+            const float2 u = uniform_sample(noise_seed, n);
+            v.x += noise_amp * u.x;
+            v.y += noise_amp * u.y;
+        }
+        out[i] = v;
+    }
+}
+int launch_synth_comb(float2* out, long long start, long long count, long long fs, int nch, long long spacing, double dev,
+                      double amp, double noise_amp, unsigned long long noise_seed, cudaStream_t s) {
+    if (count <= 0) return 0;
+    synth_comb_kernel<<<stream_grid(count, 256, 8), 256, 0, s>>>(out, start, count, fs, nch, spacing, (float)dev, (float)amp,
+                                                                 (float)noise_amp, noise_seed);
+    QDSP_LAUNCH_OK();
+    return 0;
+}
+// BASELINE config 5 inputs (synth.py qpsk_cf32): QPSK symbols held for sps samples, rotated by freq_off rad/sample,
+// slow amplitude modulation (depth, period), + sigma * U(seed, n).
+__global__ void __launch_bounds__(256) synth_qpsk_kernel(float2* __restrict__ out, long long start, long long count,
+                                                        unsigned long long seed, int sps, double freq_off, float sigma,
+                                                        float am_depth, long long am_period) {
+    const double two_pi = 6.283185307179586476925286766559;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += stride) {
+        const long long n = start + i;
+        const uint64_t sym = splitmix64(((seed + 77ull) << 40) ^ (uint64_t)(n / sps));
+        const int bits = (int)(sym & 3ull);
+        double ph = 0.78539816339744830962 + 1.57079632679489661923 * bits + fmod(freq_off * (double)n, two_pi);
+        double sn, cs;
+        sincos(ph, &sn, &cs);
+        double a = 1.0;
+        if (am_depth != 0.0f) a += (double)am_depth * sin(two_pi * (double)(n % am_period) / (double)am_period);
+        const float2 u = uniform_sample(seed, n);
+        out[i] = make_float2((float)(a * cs) + sigma * u.x, (float)(a * sn) + sigma * u.y);
+    }
+}
+int launch_synth_qpsk(float2* out, long long start, long long count, unsigned long long seed, int sps, double freq_off,
+                      double sigma, double am_depth, long long am_period, cudaStream_t s) {
+    if (count <= 0) return 0;
+    synth_qpsk_kernel<<<stream_grid(count, 256, 8), 256, 0, s>>>(out, start, count, seed, sps, freq_off, (float)sigma,
+                                                                 (float)am_depth, am_period > 0 ? am_period : 1);
+    QDSP_LAUNCH_OK();
+    return 0;
+}
+
 // ---- FP32 roofline denominator: FMA-saturation probe --------------------------------------------------
 template <int PACKED>
 __global__ void __launch_bounds__(512) fp32_peak_kernel(float* sink, int iters, float a, float b) {

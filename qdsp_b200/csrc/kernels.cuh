@@ -34,6 +34,10 @@ int launch_power_decim(const float2* in, float2* out, long long n_out, int copy_
 int launch_synth_uniform(float2* out, unsigned long long seed, long long start, long long count, cudaStream_t s);
 int launch_synth_fm(float2* out, long long start, long long count, long long fs, long long fc, long long fm,
                     double dev, double amp, double noise_amp, unsigned long long noise_seed, cudaStream_t s);
+int launch_synth_comb(float2* out, long long start, long long count, long long fs, int nch, long long spacing, double dev,
+                      double amp, double noise_amp, unsigned long long noise_seed, cudaStream_t s);
+int launch_synth_qpsk(float2* out, long long start, long long count, unsigned long long seed, int sps, double freq_off,
+                      double sigma, double am_depth, long long am_period, cudaStream_t s);
 double run_fp32_peak(int packed, int iters);
 
 // ---- k_decim.cu: column-parallel decimating FIR (I = 1, even D), optional NCO + FM demod --------

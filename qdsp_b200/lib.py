@@ -194,6 +194,8 @@ SIGNATURES = {
     "qdsp_sinesource_process": (_ll, [_vp, _vp, _ll, _vp]),
     "qdsp_synth_uniform_cf32": (_i, [_vp, _ull, _ll, _ll, _vp]),
     "qdsp_synth_fm_cf32": (_i, [_vp, _ll, _ll, _ll, _ll, _ll, _d, _d, _d, _ull, _vp]),
+    "qdsp_synth_comb_cf32": (_i, [_vp, _ll, _ll, _ll, _i, _ll, _d, _d, _d, _ull, _vp]),
+    "qdsp_synth_qpsk_cf32": (_i, [_vp, _ll, _ll, _ull, _i, _d, _d, _d, _ll, _vp]),
     "qdsp_measure_fp32_peak": (_d, [_i, _i]),
 }
 

@@ -67,30 +67,26 @@ def halo_sources(shards: list[TimeShard], rank: int) -> list[tuple[int, int, int
 
 
 def exchange_halo(shards: list[TimeShard], rank: int, local, history: int, dist):
-    """Ring-shift the history tails with point-to-point sends (gloo on CPU tensors in tests, NCCL over NVLink on
-    the GPU box). `local` is this rank's shard as a torch tensor of complex64 (any device); returns a tensor of
-    `history` samples: zeros, then whatever precedes the shard. No collective, one small message per rank pair."""
+    """Ring-shift the history tails with point-to-point sends (gloo on CPU tensors in tests; on a GPU box this is the
+    FALLBACK path -- bench.py's config 3 lets the FIR kernel read the neighbour's tail directly through a CUDA-IPC peer
+    mapping, qdsp_ipc_open + qdsp_fir_process_halo, with no message at all). `local` is this rank's shard as a torch
+    tensor of complex64 (any device); returns a tensor of `history` samples: zeros, then whatever precedes the shard.
+    The tails travel as float32 VIEWS of the shard (no staging copies), one message per rank pair."""
     import torch
 
     halo = torch.zeros(history, dtype=local.dtype, device=local.device)
+    halo_f = torch.view_as_real(halo)            # [history, 2] float32 view: received straight into place
+    local_f = torch.view_as_real(local)
     world = len(shards)
     reqs = []
-    # post receives first (halo is written right-aligned: the newest sample sits at halo[-1])
-    pos = history - shards[rank].halo
-    recv_views = []
+    pos = history - shards[rank].halo            # right-aligned: the newest sample sits at halo[-1]
     for src, _, n in halo_sources(shards, rank):
-        buf = torch.empty(n, dtype=torch.float32, device=local.device).repeat(2).reshape(2, n).contiguous()
-        recv_views.append((pos, n, buf))
-        reqs.append(dist.irecv(buf, src=src))
+        reqs.append(dist.irecv(halo_f[pos:pos + n], src=src))
         pos += n
     for dst in range(rank + 1, world):
         for src, off, n in halo_sources(shards, dst):
             if src == rank:
-                seg = local[off:off + n]
-                payload = torch.stack([seg.real, seg.imag]).contiguous()
-                reqs.append(dist.isend(payload, dst=dst))
+                reqs.append(dist.isend(local_f[off:off + n], dst=dst))
     for r in reqs:
         r.wait()
-    for pos, n, buf in recv_views:
-        halo[pos:pos + n] = torch.complex(buf[0], buf[1])
     return halo
