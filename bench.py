@@ -621,7 +621,9 @@ def run_cfg4(cx: Ctx, fp32_peak):
     L, lib = cx.L, cx.lib
     n, nch_total = cx.args.n4, 256
     fs, spacing = 61_440_000, 240_000
-    sl = shard.channel_slice(nch_total, cx.world, cx.rank)
+    # --cfg4-world W (development aid): take rank 0's share of a W-way partition on this one GPU (32 channels for W = 8)
+    eworld = cx.args.cfg4_world if (cx.args.cfg4_world and cx.world == 1) else cx.world
+    sl = shard.channel_slice(nch_total, eworld, cx.rank)
     offs_all = synth.cfg4_offsets(nch_total, spacing)
     offs = offs_all[sl]
     nch = len(offs)
@@ -652,6 +654,8 @@ def run_cfg4(cx: Ctx, fp32_peak):
         worst = max(worst, w)
         cnt += k2
     worst = cx.allmax(worst)
+    if eworld != cx.world:      # emulated share: report this GPU's channels only
+        nch_total = nch
     tf = 38.0 * nch_total * n / ms / 1e9
     res = {"workload": f"{nch_total}-channel channelizer (VFO + FloatFMDemod per channel: 10241 taps, I=1, D=1280) off one 61.44 MS/s stream of "
                        f"{n} cf32; {nch} channels on each of {cx.world} GPU(s), no collective",
@@ -816,6 +820,7 @@ def main():
     ap.add_argument("--configs", default="1,3,4,5", help="other BASELINE configs to run after the headline (subset of 1,3,4,5; '' = none)")
     ap.add_argument("--n3", type=int, default=1 << 30, help="config 3 stream length (BASELINE: 2^30)")
     ap.add_argument("--n4", type=int, default=1 << 26, help="config 4 wideband stream length (BASELINE: 2^26)")
+    ap.add_argument("--cfg4-world", type=int, default=0, help="development aid: run rank 0's channel share of a W-GPU partition on one GPU")
     ap.add_argument("--n5", type=int, default=1 << 28, help="config 5 stream length (BASELINE: 2^28)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -558,6 +558,11 @@ struct qdsp_channelizer {
                                       (const float2*)in_dev, part, 1, nco_dev, &nh, abs_pos, phasor_speed, din, dout,
                                       (float2*)iq, audio, rpad, s);
             hist_folded = rc == 0;
+        } else if (plan && variant != 1 && chan_supported(plan) && (reinterpret_cast<uintptr_t>(in_dev) & 15) == 0 &&
+                   part.max_out > 0 && (rpad = rowlane_uniform_pad(part, T)) >= 0) {
+            // wide rows: channel-per-lane kernel (32 channels share every staged sample), one launch per column slice
+            rc = launch_chan(plan, taps.data(), (const float2*)hist.ptr(), hist.H, (const float2*)in_dev, part, 1, nco_dev,
+                             abs_pos, nch, phasor_speed, din, dout, (float2*)iq, audio, out_stride, rpad, s);
         } else if (plan && variant != 1)
             rc = launch_decim(plan, (const float2*)hist.ptr(), hist.H, (const float2*)in_dev, part, 1, nco_dev,
                               abs_pos, nch, phasor_speed, din, dout, (float2*)iq, audio, out_stride, s);

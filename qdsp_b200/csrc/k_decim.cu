@@ -815,6 +815,7 @@ DecimPlan* decim_plan_create(const float* taps, int T, int D) {
 }
 void decim_plan_destroy(DecimPlan* p) {
     if (!p) return;
+    chan_plan_released(p);
     if (p->taps_dev) cudaFree(p->taps_dev);
     if (p->ypart) cudaFree(p->ypart);
     delete p;
@@ -853,6 +854,18 @@ __global__ void __launch_bounds__(256) decim_finish_kernel(const float2* __restr
             if (o == total_out - 1) demod_out[ch] = cur;
         }
     }
+}
+
+int launch_decim_finish(const float2* ypart, long long ypart_stride, int nslices, long long total_out, int demod,
+                        float phasor_speed, const float* demod_in, float* demod_out, float2* out_iq, float* audio,
+                        long long out_stride, int nch, cudaStream_t s) {
+    if (total_out <= 0) return 0;
+    long long gx = (total_out + 255) / 256;
+    if (gx > 1024) gx = 1024;
+    decim_finish_kernel<<<dim3((unsigned)gx, nch), 256, 0, s>>>(ypart, ypart_stride, nslices, total_out, demod, phasor_speed,
+                                                                 demod_in, demod_out, out_iq, audio, out_stride);
+    QDSP_LAUNCH_OK();
+    return 0;
 }
 
 template <int Q, int DT, int NSEGT, bool ROT, bool DEMOD, bool SUPRED>

@@ -58,6 +58,16 @@ int launch_decim_rowlane(DecimPlan* plan, const float* taps_host, const float2* 
                          long long abs0, float phasor_speed, const float* demod_in, float* demod_out, float2* out_iq,
                          float* audio, int pad, cudaStream_t s);
 
+// ---- k_chan.cu: channel-per-lane decimating FIR (wide rows, many channels off one input) --------------------
+bool chan_supported(const DecimPlan* plan);
+void chan_plan_released(const DecimPlan* plan);
+int launch_chan(DecimPlan* plan, const float* taps_host, const float2* hist, int H, const float2* in, const Partition& part,
+                int mode, const NcoDev* nco_dev, long long abs0, int nch, float phasor_speed, const float* demod_in,
+                float* demod_out, float2* out_iq, float* audio, long long out_stride, int pad, cudaStream_t s);
+int launch_decim_finish(const float2* ypart, long long ypart_stride, int nslices, long long total_out, int demod,
+                        float phasor_speed, const float* demod_in, float* demod_out, float2* out_iq, float* audio,
+                        long long out_stride, int nch, cudaStream_t s);
+
 // ---- k_fir.cu: register-blocked dense FIR (cf32, D = 1) -----------------------------------------
 struct FirPlan;
 FirPlan* fir_plan_create(const float* taps, int T);
