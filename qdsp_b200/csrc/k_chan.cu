@@ -40,10 +40,11 @@ struct ChanArgs {
 // SLICE < 0: run-time slice (blockIdx.z), the slice's 8 x DC taps are staged in shared memory and read with broadcast
 // loads -- one body for every slice, used when few channel groups run per GPU (the immediate-tap bodies of different
 // slices would otherwise be resident together and thrash the instruction cache: ncu `no_instructions` stalls).
-template <int DS, int DC, bool ROT, int SLICE>
+template <int DS, int DC, bool ROT, int SLICE, int NR = 1>
 __device__ __forceinline__ void chan_body(const ChanArgs& ca) {
     constexpr int PAIRS = DC / 2;
-    constexpr int RS = 4;                       // rows per ring stage
+    constexpr int RS = 4;                       // rows per ring stage (a multiple of NR)
+    static_assert(RS % NR == 0, "rows per step");
     constexpr int NSTG = 4;                     // ring depth
     constexpr uint32_t ROW_BYTES = DC * 8u;
     constexpr uint32_t STAGE_BYTES = RS * ROW_BYTES;
@@ -134,35 +135,45 @@ __device__ __forceinline__ void chan_body(const ChanArgs& ca) {
         const int slot = st % NSTG;
         mbar_wait(&mbar[slot], (uint32_t)((st / NSTG) & 1));
 #pragma unroll 1
-        for (int rr = 0; rr < RS; rr++) {
+        for (int rr = 0; rr < RS; rr += NR) {
             const int r = st * RS + rr;
             if (r >= nrows) break;
-            const float4* xrow = reinterpret_cast<const float4*>(smem_raw + slot * STAGE_BYTES + rr * ROW_BYTES);
-            float2 PR = make_float2(1.f, 1.f), PI = make_float2(0.f, 0.f);
-            if (ROT) {
-                const long long n0 = row0 + (long long)r * DS;
-                const float2 p0 = phasor_from_turns(nco_ph0 + nco_step * (uint64_t)n0);
-                const float2 p1 = cmul(p0, w1);
-                PR = make_float2(p0.x, p1.x);
-                PI = make_float2(p0.y, p1.y);
+            // NR rows per step: one set of tap loads feeds the FFMA2s of NR rows (halves the tap traffic for NR = 2)
+            const float4* xrow[NR];
+            float2 PR[NR], PI[NR];
+#pragma unroll
+            for (int j = 0; j < NR; j++) {
+                xrow[j] = reinterpret_cast<const float4*>(smem_raw + slot * STAGE_BYTES + (rr + j) * ROW_BYTES);
+                PR[j] = make_float2(1.f, 1.f);
+                PI[j] = make_float2(0.f, 0.f);
+                if (ROT) {
+                    const long long n0 = row0 + (long long)(r + j) * DS;
+                    const float2 p0 = phasor_from_turns(nco_ph0 + nco_step * (uint64_t)n0);
+                    const float2 p1 = cmul(p0, w1);
+                    PR[j] = make_float2(p0.x, p1.x);
+                    PI[j] = make_float2(p0.y, p1.y);
+                }
             }
-            float2 aRe[8], aIm[8];
-            float2 sRe = make_float2(0.f, 0.f), sIm = make_float2(0.f, 0.f);
+            float2 aRe[NR][8], aIm[NR][8];
+            float2 sRe[NR], sIm[NR];
 #pragma unroll
             for (int c = 0; c < PAIRS; c++) {
-                const float4 v = xrow[c];
-                float2 RE, IM;
-                if (ROT) {
-                    RE.x = fmaf(v.x, PR.x, -(v.y * PI.x));
-                    IM.x = fmaf(v.x, PI.x, v.y * PR.x);
-                    RE.y = fmaf(v.z, PR.y, -(v.w * PI.y));
-                    IM.y = fmaf(v.z, PI.y, v.w * PR.y);
-                    const float2 nPR = __ffma2_rn(PI, nwi2, __fmul2_rn(PR, wr2));
-                    PI = __ffma2_rn(PI, wr2, __fmul2_rn(PR, wi2));
-                    PR = nPR;
-                } else {
-                    RE = make_float2(v.x, v.z);
-                    IM = make_float2(v.y, v.w);
+                float2 RE[NR], IM[NR];
+#pragma unroll
+                for (int j = 0; j < NR; j++) {
+                    const float4 v = xrow[j][c];
+                    if (ROT) {
+                        RE[j].x = fmaf(v.x, PR[j].x, -(v.y * PI[j].x));
+                        IM[j].x = fmaf(v.x, PI[j].x, v.y * PR[j].x);
+                        RE[j].y = fmaf(v.z, PR[j].y, -(v.w * PI[j].y));
+                        IM[j].y = fmaf(v.z, PI[j].y, v.w * PR[j].y);
+                        const float2 nPR = __ffma2_rn(PI[j], nwi2, __fmul2_rn(PR[j], wr2));
+                        PI[j] = __ffma2_rn(PI[j], wr2, __fmul2_rn(PR[j], wi2));
+                        PR[j] = nPR;
+                    } else {
+                        RE[j] = make_float2(v.x, v.z);
+                        IM[j] = make_float2(v.y, v.w);
+                    }
                 }
                 float4 gq[4];
                 if (SLICE < 0) {
@@ -178,28 +189,37 @@ __device__ __forceinline__ void chan_body(const ChanArgs& ca) {
                     } else {
                         g = (q & 1) ? make_float2(gq[q >> 1].z, gq[q >> 1].w) : make_float2(gq[q >> 1].x, gq[q >> 1].y);
                     }
-                    if (c == 0) {
-                        aRe[q] = __fmul2_rn(RE, g);
-                        aIm[q] = __fmul2_rn(IM, g);
-                    } else {
-                        aRe[q] = __ffma2_rn(RE, g, aRe[q]);
-                        aIm[q] = __ffma2_rn(IM, g, aIm[q]);
+#pragma unroll
+                    for (int j = 0; j < NR; j++) {
+                        if (c == 0) {
+                            aRe[j][q] = __fmul2_rn(RE[j], g);
+                            aIm[j][q] = __fmul2_rn(IM[j], g);
+                        } else {
+                            aRe[j][q] = __ffma2_rn(RE[j], g, aRe[j][q]);
+                            aIm[j][q] = __ffma2_rn(IM[j], g, aIm[j][q]);
+                        }
                     }
                 }
                 if (c == 0) {
-                    sRe = __fmul2_rn(RE, g8);
-                    sIm = __fmul2_rn(IM, g8);
+#pragma unroll
+                    for (int j = 0; j < NR; j++) {
+                        sRe[j] = __fmul2_rn(RE[j], g8);
+                        sIm[j] = __fmul2_rn(IM[j], g8);
+                    }
                 }
             }
-            // outputs in flight: output (r - q) takes this row's S_q
-            const float2 s8 = make_float2(sRe.x + sRe.y, sIm.x + sIm.y);
-            const float2 y = __fadd2_rn(O[7], s8);                 // output r - 8 is complete
+            // outputs in flight: output (row - q) takes that row's S_q
 #pragma unroll
-            for (int q = 7; q >= 1; q--)
-                O[q] = __fadd2_rn(O[q - 1], make_float2(aRe[q].x + aRe[q].y, aIm[q].x + aIm[q].y));
-            O[0] = make_float2(aRe[0].x + aRe[0].y, aIm[0].x + aIm[0].y);
-            const int k = r - 8;
-            if (k >= 0 && k < nout && ch_ok) plane[k] = y;
+            for (int j = 0; j < NR; j++) {
+                const float2 s8 = make_float2(sRe[j].x + sRe[j].y, sIm[j].x + sIm[j].y);
+                const float2 y = __fadd2_rn(O[7], s8);                 // output row - 8 is complete
+#pragma unroll
+                for (int q = 7; q >= 1; q--)
+                    O[q] = __fadd2_rn(O[q - 1], make_float2(aRe[j][q].x + aRe[j][q].y, aIm[j][q].x + aIm[j][q].y));
+                O[0] = make_float2(aRe[j][0].x + aRe[j][0].y, aIm[j][0].x + aIm[j][0].y);
+                const int k = r + j - 8;
+                if (k >= 0 && k < nout && ch_ok) plane[k] = y;
+            }
         }
         __syncwarp();
         issue(st + NSTG);
@@ -219,9 +239,9 @@ template <int DS, int DC, bool ROT>
 __global__ void __launch_bounds__(32) chan_kernel(const __grid_constant__ ChanArgs ca) {
     chan_dispatch<DS, DC, ROT, 0>((int)blockIdx.z, ca);
 }
-template <int DS, int DC, bool ROT>
+template <int DS, int DC, bool ROT, int NRT>
 __global__ void __launch_bounds__(32) chan_smemtaps_kernel(const __grid_constant__ ChanArgs ca) {
-    chan_body<DS, DC, ROT, -1>(ca);
+    chan_body<DS, DC, ROT, -1, NRT>(ca);
 }
 
 // ---- host side -------------------------------------------------------------------------------------
@@ -283,7 +303,8 @@ static int launch_chan_t(DecimPlan* plan, const float* taps_host, const float2* 
     ca.taps_dev = g_chan_taps_dev;
     // outputs per segment (CTA): enough single-warp CTAs to fill the machine several times over; the halo is 8 rows
     static const int seg_env = getenv("QDSP_CHAN_SEG") ? atoi(getenv("QDSP_CHAN_SEG")) : 0;
-    ca.seg_rows = seg_env > 0 ? seg_env : 160;
+    // B200, 2^26 samples (GS/s wideband): 32 ch (1 group): 80: 27.0, 128: 31.0, 160: 29.3, 320: 29.5; 256 ch: 128: 4.41, 160: 4.44, 320: 3.69
+    ca.seg_rows = seg_env > 0 ? seg_env : (ca.groups < 4 ? 128 : 160);
     dim3 grid((part.max_out + ca.seg_rows - 1) / ca.seg_rows, part.view.nblocks * ca.groups, ca.nslices);
     if (grid.y > 65535) {
         set_last_error("chan: too many run() blocks x channel groups (%u)", grid.y);
@@ -294,8 +315,13 @@ static int launch_chan_t(DecimPlan* plan, const float* taps_host, const float2* 
     static const int smt_env = getenv("QDSP_CHAN_SMEMTAPS") ? atoi(getenv("QDSP_CHAN_SMEMTAPS")) : -1;
     const bool smemtaps = smt_env >= 0 ? smt_env != 0 : ca.groups < 4;
     constexpr size_t smem = 4 * 4 * DC * 8 + 64 + 8 * DC * 4 + 64;
-    if (rot && smemtaps) {
-        auto kern = chan_smemtaps_kernel<DS, DC, true>;
+    static const int nr_env = getenv("QDSP_CHAN_NR") ? atoi(getenv("QDSP_CHAN_NR")) : 2;
+    if (rot && smemtaps && nr_env == 2) {
+        auto kern = chan_smemtaps_kernel<DS, DC, true, 2>;
+        QDSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 32, smem, s>>>(ca);
+    } else if (rot && smemtaps) {
+        auto kern = chan_smemtaps_kernel<DS, DC, true, 1>;
         QDSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, 32, smem, s>>>(ca);
     } else if (rot) {
