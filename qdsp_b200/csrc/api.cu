@@ -226,6 +226,7 @@ struct qdsp_resamp {
     DecimPlan* plan = nullptr;
     FirDecimPlan* fplan = nullptr;   // small decimation (2..8): dense polyphase kernel
     int variant = 0;
+    std::vector<float> taps;         // host copy (kernels that take their taps as launch parameters)
 };
 
 extern "C" {
@@ -259,6 +260,7 @@ int qdsp_resamp_set_taps(qdsp_resamp* h, const float* taps, int tapCount) {
     std::vector<float> ph = build_phases(taps, tapCount, h->interp, &tpp);
     if (upload_floats(&h->phases_dev, ph) != 0) return -1;
     h->T = tapCount;
+    h->taps.assign(taps, taps + tapCount);
     if (tpp != h->tpp) {
         h->tpp = tpp;
         if (h->hist.init(tpp, h->dtype == QDSP_CF32 ? 8 : 4) != 0) return -1;  // zeroed, resampling.h:39
@@ -302,7 +304,14 @@ long long qdsp_resamp_process(qdsp_resamp* h, const void* in_dev, void* out_dev,
             regular = h->part.view.nblocks <= 1 || (h->part.view.block_size % h->decim) == 0;
         }
     }
-    if (regular) {
+    if (regular && h->variant != 2 && firrow_supported(h->T, h->decim) && (reinterpret_cast<uintptr_t>(in_dev) & 15) == 0) {
+        // config 1b's geometry: row-per-lane kernel (TMA-fed, taps as uniform-register operands)
+        rc = launch_firrow(h->taps.data(), h->T, h->decim, (const float2*)h->hist.ptr(), (float2*)h->hist.buf[h->hist.cur ^ 1],
+                           h->hist.H, (const float2*)in_dev, count, h->part.total_out, (float2*)out_dev, s);
+        if (rc != 0) return -1;
+        h->hist.cur ^= 1;            // the kernel's first CTA advanced the history tail
+        return h->part.total_out;
+    } else if (regular) {
         rc = launch_fir_decim(h->fplan, (const float2*)h->hist.ptr(), h->hist.H, (const float2*)in_dev, count,
                               h->part.total_out, (float2*)out_dev, s);
     } else if (h->plan && h->variant != 1) {

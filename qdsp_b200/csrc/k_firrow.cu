@@ -1,0 +1,264 @@
+// qdsp_b200/csrc/k_firrow.cu — row-per-lane decimating FIR for SMALL decimations (PolyphaseResampler<complex_t> with
+// interp = 1, D = 4: BASELINE config 1b, reference resampling.h:99-132), the small-D sibling of k_rowlane.cu.
+//
+// The stream is cut into rows of DROW = 28 samples = NPH = DROW / D = 7 outputs. Output k = NPH*r + j (row r, phase j) is
+//     y[k] = sum_q S_{j,q}(r + q),   S_{j,q}(row) = sum_{c < DROW} g_j[q*DROW + c] * x[row, c],   g_j[u] = h[u - j*D - pad]
+// i.e. NPH decimate-by-DROW filters whose taps are shifted copies of h (Q = 6 tap rows cover the 127 + 24 + 1 window).
+// Lane l of a step owns row 32*i + l and computes all NPH x Q row partials of its 28 samples (kept in registers as 14
+// (re,re)/(im,im) column pairs): the tap pairs are compile-time offsets into the kernel-parameter constant bank ->
+// uniform-register FFMA2 operands (one 128-bit constant load per 4 FFMA2), dead (zero) tap pairs are skipped at compile
+// time (T is a template parameter): 32.3 FFMA2 per input sample against the algorithmic 31.75. Output (r, j) then gathers
+// its Q partials from lanes r .. r+Q-1 with shuffles; lanes whose window runs past lane 31 finish one step later (as in
+// k_rowlane.cu). No shared-memory exchange, no CTA barrier; a CTA is one warp with its own TMA ring, one bulk copy of 32
+// contiguous rows per stage. The 224-byte row pitch makes the per-lane 128-bit loads 2-way bank conflicted (14 loads per
+// 760 FFMA2: irrelevant); 16-sample rows (128-byte pitch) would need one padded copy per row, and ncu showed the
+// per-copy issue sequence eating 20 % of the instruction slots.
+#include <math.h>
+#include <mutex>
+#include <new>
+#include "decim_common.cuh"
+
+namespace qdsp {
+
+// packed f32x2 values as opaque 64-bit registers: built once per column pair, never re-materialised from their halves
+// (with float2 temporaries ptxas re-packs the (re, re) pairs in front of nearly every FFMA2: 880 MOVs per 512 FFMA2)
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pk2(float a, float b) {
+    f32x2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    asm volatile("" : "+l"(r));
+    return r;
+}
+__device__ __forceinline__ float2 unpk2(f32x2_t v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ f32x2_t ffma2x(f32x2_t a, f32x2_t b, f32x2_t c) {
+    f32x2_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2_t fmul2x(f32x2_t a, f32x2_t b) {
+    f32x2_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+template <int NPH, int Q, int DROW>
+struct FirRowArgs {
+    const float2* hist;
+    const float2* in;
+    int H;
+    long long count;          // input samples of this call
+    long long n_out;          // outputs of this call
+    int T, pad;
+    int nstep;                // steps (of 32 rows) per tile
+    float2* out;
+    float2* hist_next;        // when non-null: CTA 0 writes the advanced history tail here (resampling.h:129)
+    alignas(16) float g[NPH][Q * DROW];   // g[j][u] = h[u - j*D - pad], zero outside
+};
+
+// is the tap pair (columns 2c, 2c+1 of tap row q) of phase j live for T taps?
+__host__ __device__ constexpr bool firrow_live(int j, int q, int c, int D, int DROW, int pad, int T) {
+    const int u0 = q * DROW + 2 * c, lo = j * D + pad, hi = j * D + pad + T;
+    return u0 + 2 > lo && u0 < hi;
+}
+__host__ __device__ constexpr int firrow_first(int j, int q, int D, int DROW, int pad, int T) {
+    for (int c = 0; c < DROW / 2; c++)
+        if (firrow_live(j, q, c, D, DROW, pad, T)) return c;
+    return -1;
+}
+
+template <int D, int DROW, int Q, int T, int PAD, int NSTG>
+__global__ void __launch_bounds__(32) fir_rowphase_kernel(const __grid_constant__ FirRowArgs<DROW / D, Q, DROW> fa) {
+    constexpr int NPH = DROW / D;
+    constexpr int P = DROW / 2;
+    constexpr int PITCH = DROW * 8;                         // bytes: rows stay contiguous (one bulk copy per stage)
+    constexpr uint32_t STAGE_BYTES = 32u * PITCH;
+    static_assert(DROW % D == 0 && (DROW % 4) == 0 && ((PITCH / 16) % 4) != 0, "geometry: at most 2-way bank conflicts");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x;
+    const int rows_per_tile = 32 * fa.nstep - (Q - 1);
+    const long long row_t0 = (long long)blockIdx.x * rows_per_tile;          // first row of the tile
+    const long long nrows_total = (fa.n_out + NPH - 1) / NPH;
+    if (fa.hist_next != nullptr && blockIdx.x == 0) {     // folded history advance: new_hist[j] = virtual[count - H + j]
+        for (int j = lane; j < fa.H; j += 32) {
+            const long long v = fa.count - fa.H + j;
+            fa.hist_next[j] = v >= 0 ? fa.in[v] : fa.hist[fa.H + v];
+        }
+    }
+    if (row_t0 >= nrows_total) return;
+    const long long left = nrows_total - row_t0;
+    const int nrows_emit = left < rows_per_tile ? (int)left : rows_per_tile;
+    const int nsteps = (nrows_emit + (Q - 1) + 31) / 32;
+    const long long base = -(long long)fa.T - PAD + row_t0 * DROW;           // sample index of (tile row 0, column 0)
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + NSTG * STAGE_BYTES);
+    if (lane == 0) {
+        for (int s = 0; s < NSTG; s++) mbar_init(&mbar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    auto issue = [&](int i) {
+        if (i >= nsteps) return;
+        const int slot = i % NSTG;
+        unsigned char* dst = smem_raw + slot * STAGE_BYTES;
+        const long long s0 = base + (long long)i * (32 * DROW);
+        if (s0 >= 0 && s0 + 32 * DROW <= fa.count) {
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&mbar[slot], STAGE_BYTES);
+                tma_bulk_g2s(dst, fa.in + s0, STAGE_BYTES, &mbar[slot]);
+            }
+        } else {   // history before sample 0 / ragged end: guarded fill
+            VStream<float2> xs{fa.hist, fa.in, fa.H};
+            for (int e = lane; e < 32 * DROW; e += 32) {
+                const int rr = e / DROW, cc = e - rr * DROW;
+                const long long idx = s0 + e;
+                reinterpret_cast<float2*>(dst + rr * PITCH)[cc] = idx < fa.count ? xs.at(idx) : make_float2(0.f, 0.f);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&mbar[slot]);
+        }
+    };
+    for (int i = 0; i < NSTG; i++) issue(i);
+
+    float2 old[NPH];
+#pragma unroll
+    for (int j = 0; j < NPH; j++) old[j] = make_float2(0.f, 0.f);
+    const bool tail_lane = lane >= 32 - (Q - 1);
+
+#pragma unroll 1
+    for (int i = 0; i < nsteps; i++) {
+        const int slot = i % NSTG;
+        mbar_wait(&mbar[slot], (uint32_t)((i / NSTG) & 1));
+        const float4* xrow = reinterpret_cast<const float4*>(smem_raw + slot * STAGE_BYTES + lane * PITCH);
+        f32x2_t RE[P], IM[P];
+#pragma unroll
+        const f32x2_t one2 = pk2(1.0f, 1.0f);
+        for (int c = 0; c < P; c++) {
+            const float4 v = xrow[c];
+            // x * 1 is exact; the multiply makes the (re, re) / (im, im) pair the RESULT of an instruction, which ptxas keeps
+            // in a register pair (a bare pack of two loaded halves it re-creates with two MOVs before every use)
+            RE[c] = fmul2x(pk2(v.x, v.z), one2);
+            IM[c] = fmul2x(pk2(v.y, v.w), one2);
+        }
+        __syncwarp();
+        issue(i + NSTG);
+        float2 yv[NPH];
+#pragma unroll
+        for (int j0 = 0; j0 < NPH; j0 += 2) {           // two phases per pass: 2 x Q x 2 packed accumulators
+            constexpr int NJ = 2;
+            f32x2_t aRe[NJ][Q], aIm[NJ][Q];
+#pragma unroll
+            for (int c2 = 0; c2 < P / 2; c2++) {        // two column pairs per 128-bit constant-bank tap load
+#pragma unroll
+                for (int jj = 0; jj < NJ; jj++) {
+                    if (j0 + jj >= NPH) continue;
+#pragma unroll
+                    for (int q = 0; q < Q; q++) {
+                        const bool l0 = firrow_live(j0 + jj, q, 2 * c2, D, DROW, PAD, T);
+                        const bool l1 = firrow_live(j0 + jj, q, 2 * c2 + 1, D, DROW, PAD, T);
+                        if (l0 || l1) {
+                            const ulonglong2 g2 = *reinterpret_cast<const ulonglong2*>(&fa.g[j0 + jj][q * DROW + 4 * c2]);
+#pragma unroll
+                            for (int hh = 0; hh < 2; hh++) {
+                                const int c = 2 * c2 + hh;
+                                if (hh == 0 ? l0 : l1) {
+                                    const f32x2_t g = hh ? g2.y : g2.x;
+                                    if (c == firrow_first(j0 + jj, q, D, DROW, PAD, T)) {
+                                        aRe[jj][q] = fmul2x(RE[c], g);
+                                        aIm[jj][q] = fmul2x(IM[c], g);
+                                    } else {
+                                        aRe[jj][q] = ffma2x(RE[c], g, aRe[jj][q]);
+                                        aIm[jj][q] = ffma2x(IM[c], g, aIm[jj][q]);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            // row partials -> outputs: output (row, j) takes S_{j,q} from lane row + q
+#pragma unroll
+            for (int jj = 0; jj < NJ; jj++) {
+                const int j = j0 + jj;
+                if (j >= NPH) continue;
+                float2 cur = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < Q; q++) {
+                    if (firrow_first(j, q, D, DROW, PAD, T) >= 0) {
+                        const float2 ar = unpk2(aRe[jj][q]), ai = unpk2(aIm[jj][q]);
+                        const float2 s = make_float2(ar.x + ar.y, ai.x + ai.y);
+                        if (q == 0) {
+                            cur = s;
+                        } else {
+                            float2 p;
+                            p.x = __shfl_sync(0xffffffffu, s.x, (lane + q) & 31);
+                            p.y = __shfl_sync(0xffffffffu, s.y, (lane + q) & 31);
+                            if (lane + q < 32) cur = __fadd2_rn(cur, p);
+                            else old[j] = __fadd2_rn(old[j], p);
+                        }
+                    }
+                }
+                yv[j] = tail_lane ? old[j] : cur;
+                if (tail_lane) old[j] = cur;
+            }
+        }
+        const int rrel = 32 * i + lane - (tail_lane ? 32 : 0);          // tile-relative row of the outputs just finished
+        if (rrel >= 0 && rrel < nrows_emit) {
+            const long long k = (row_t0 + rrel) * NPH;
+            float2* o = fa.out + k;
+#pragma unroll
+            for (int j = 0; j < NPH; j++)
+                if (k + j < fa.n_out) o[j] = yv[j];
+        }
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+bool firrow_supported(int T, int D) {
+    static const bool on = getenv("QDSP_FIRROW") ? atoi(getenv("QDSP_FIRROW")) != 0 : true;
+    return on && D == 4 && T == 127;
+}
+
+int launch_firrow(const float* taps_host, int T, int D, const float2* hist, float2* hist_next, int H, const float2* in,
+                  long long count, long long n_out, float2* out, cudaStream_t s) {
+    if (n_out <= 0) return 0;
+    constexpr int DROW = 28, Q = 6, NPH = 7, NSTG = 3;
+    if (!firrow_supported(T, D) || (reinterpret_cast<uintptr_t>(in) & 15) != 0) {
+        set_last_error("firrow: unsupported geometry");
+        return -1;
+    }
+    static FirRowArgs<NPH, Q, DROW> fa;
+    static std::mutex mtx;
+    std::lock_guard<std::mutex> lk(mtx);
+    constexpr int PAD = 1;                       // T odd: the window starts one sample early so that rows are 16-byte aligned
+    fa.hist = hist;
+    fa.in = in;
+    fa.H = H;
+    fa.count = count;
+    fa.n_out = n_out;
+    fa.T = T;
+    fa.pad = PAD;
+    static const int nstep_env = getenv("QDSP_FIRROW_NSTEP") ? atoi(getenv("QDSP_FIRROW_NSTEP")) : 0;
+    fa.nstep = nstep_env >= 2 ? nstep_env : 3;
+    fa.out = out;
+    fa.hist_next = hist_next;
+    for (int j = 0; j < NPH; j++)
+        for (int u = 0; u < Q * DROW; u++) {
+            const int t = u - j * D - PAD;
+            fa.g[j][u] = (t >= 0 && t < T) ? taps_host[t] : 0.0f;
+        }
+    const long long nrows = (n_out + NPH - 1) / NPH;
+    const int rows_per_tile = 32 * fa.nstep - (Q - 1);
+    const long long tiles = (nrows + rows_per_tile - 1) / rows_per_tile;
+    constexpr size_t smem = NSTG * 32 * (DROW * 8) + NSTG * 8 + 16;
+    auto kern = fir_rowphase_kernel<4, DROW, Q, 127, PAD, NSTG>;
+    QDSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)tiles, 32, smem, s>>>(fa);
+    QDSP_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace qdsp
