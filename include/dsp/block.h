@@ -24,7 +24,10 @@ namespace dsp {
     template <class BLOCK>
     class generic_block : public generic_unnamed_block {
     public:
-        generic_block() { cuStream = qdsp_stream_create(); }
+        generic_block() {
+            cuDevice = qdsp_get_device();      // streams, buffers and handles live on the constructing thread's device
+            cuStream = qdsp_stream_create();
+        }
         virtual ~generic_block() {
             stop();
             qdsp_stream_destroy(cuStream);
@@ -66,6 +69,7 @@ namespace dsp {
 
         virtual void doStart() {
             worker = std::thread([this] {
+                if (cuDevice >= 0) { qdsp_set_device(cuDevice); }   // a new host thread starts on device 0
                 while (run() >= 0) {}
             });
         }
@@ -94,6 +98,7 @@ namespace dsp {
         bool paused = false;
         std::thread worker;
         qdsp_stream_t cuStream = nullptr;
+        int cuDevice = -1;
         std::mutex ctrlMtx;
     };
 

@@ -1473,6 +1473,12 @@ int qdsp_mm_set_omega_rel_limit(qdsp_mm* h, float omegaRelLimit) {   // :106-112
     return 0;
 }
 int qdsp_mm_set_speculation(qdsp_mm* h, int chunk, int warmup) {
+#ifndef QDSP_MM_SPECULATION
+    if (chunk != 0) {
+        set_last_error("qdsp_mm_set_speculation: experimental variant not compiled in (-DQDSP_MM_SPECULATION)");
+        return -1;
+    }
+#endif
     if (chunk != 0 && (warmup < 0 || chunk < warmup + 8)) {
         set_last_error("qdsp_mm_set_speculation: need chunk >= warmup + 8");
         return -1;

@@ -185,6 +185,7 @@ __device__ __forceinline__ bool mm_same(const MmLoop& a, const MmLoop& b) {
 struct MmParams {
     float gainOmega, muGain, omegaMin, omegaMax;
 };
+#ifdef QDSP_MM_SPECULATION   // experimental speculate-and-verify variant: exact, measured, does not pay; not built by default
 // one symbol: interpolate at L.i from x[i-7 .. i] (`src`, 8 elements), run the detector and the loop update
 template <bool CPLX>
 __device__ __forceinline__ float2 mm_symbol(MmLoop& L, const float* src, const float* taps, const MmParams& P) {
@@ -440,6 +441,15 @@ int launch_mm_spec(int cplx, const void* in, const Partition& part, const float*
     }
     return 0;
 }
+
+#else
+size_t mm_spec_scratch_bytes(long long, int, int) { return 0; }
+int launch_mm_spec(int, const void*, const Partition&, const float*, float, float, float, float, float*, void*, int*, long long*,
+                   int*, int, int, int, void*, cudaStream_t) {
+    set_last_error("mm: the speculate-and-verify variant is not compiled in (build with -DQDSP_MM_SPECULATION)");
+    return -1;
+}
+#endif
 
 int launch_mm(int cplx, const void* in, const Partition& part, const float* taps_dev, float omega, float gainOmega,
               float muGain, float omegaMin, float omegaMax, float* state, void* out, int* out_counts_dev,

@@ -577,6 +577,11 @@ def test_psk_demod_chain(name, golden):
 
 @pytest.mark.parametrize("dtype", ["cf32", "f32"])
 def test_clock_recovery_speculate_and_verify(dtype):
+    from qdsp_b200 import blocks as _B, lib as _qlib
+    from tests.runners import interp_taps as _taps
+    _probe = _B.MMClockRecovery(4.0, (0.01 * 0.01) / 4, 0.01, 0.005, _taps())
+    if _qlib.load().qdsp_mm_set_speculation(_probe.h, 4096, 1024) != 0:
+        pytest.skip("experimental MM speculate-and-verify variant not compiled in (-DQDSP_MM_SPECULATION)")
     # chunks walked in parallel from the default loop state, accepted only where bit-equal at the boundary: symbols,
     # per-block counts and the carried state must equal the sequential walk's whatever the speculation did -- with a
     # warm-up long enough to merge (few or no re-walks) and with a hopeless one (every chunk re-walked)
@@ -688,3 +693,31 @@ def test_rowlane_streaming_calls_carry_history_and_phase():
     assert many.shape == a64.shape
     assert np.abs(many[16:] - a64[16:]).max() <= AUDIO_TOL
     assert one.shape[0] > 0
+
+
+def test_complex_agc_lookback_long_and_streaming():
+    # the single-pass (decoupled look-back) ComplexAGC: many 8192-sample tiles, ragged end, state carried across calls
+    from qdsp_b200 import blocks as B, synth
+
+    P = loader.port()
+    n = 300_001
+    x = synth.qpsk_cf32(21, 0, n, am_depth=0.5, am_period=3000)
+    yo = P.complex_agc(1.0, 65535.0, 1e-3, x)
+    c = B.ComplexAGC(1.0, 65535.0, 1e-3)
+    y = c.process(x)
+    assert rel_l2(y, yo) <= 1e-4, rel_l2(y, yo)
+    c2 = B.ComplexAGC(1.0, 65535.0, 1e-3)
+    parts = np.concatenate([c2.process(x[:8192]), c2.process(x[8192:8193]), c2.process(x[8193:200_000]), c2.process(x[200_000:])])
+    assert rel_l2(parts, yo) <= 1e-4
+
+
+def test_costas_fast_vco_long():
+    # chunked Costas scan with the SFU sine / cosine on the loop's VCO: 2^21 QPSK samples vs the sequential oracle
+    from qdsp_b200 import blocks as B, synth
+
+    x = synth.qpsk_cf32(23, 0, 1 << 21)
+    yo, _ = loader.port().costas(4, 0.004, x)
+    pl = B.CostasLoop(4, 0.004)
+    y = pl.process(x)
+    assert pl.last_residual() < 1e-3
+    assert np.abs(y - yo).max() <= 1e-4, np.abs(y - yo).max()

@@ -143,7 +143,7 @@ def main():
             from qdsp_b200 import synth
             nq = 1 << 24
             xq = torch.from_numpy(synth.qpsk_cf32(91, 0, nq, sps=4, freq_off=0.0, sigma=0.05)).cuda()
-            for chunk, warm in ((32768, 8192),):
+            for chunk, warm in (((32768, 8192),) if os.environ.get("QDSP_BENCH_MM_SPEC") else ()):   # needs -DQDSP_MM_SPECULATION
                 mm2 = B.MMClockRecovery(4.0, (0.01 * 0.01) / 4, 0.01, 0.005, taps)
                 mm2.set_speculation(chunk, warm)
                 ms = timed(lambda: mm2.process_device(xq.data_ptr(), yp, nq, 1000000, stream=sp), 3, warmup=1)
