@@ -304,7 +304,8 @@ long long qdsp_resamp_process(qdsp_resamp* h, const void* in_dev, void* out_dev,
             regular = h->part.view.nblocks <= 1 || (h->part.view.block_size % h->decim) == 0;
         }
     }
-    if (regular && h->variant != 2 && firrow_supported(h->T, h->decim) && (reinterpret_cast<uintptr_t>(in_dev) & 15) == 0) {
+    if (regular && h->variant != 2 && h->part.total_out > 0 && firrow_supported(h->T, h->decim) &&
+        (reinterpret_cast<uintptr_t>(in_dev) & 15) == 0) {
         // config 1b's geometry: row-per-lane kernel (TMA-fed, taps as uniform-register operands)
         rc = launch_firrow(h->taps.data(), h->T, h->decim, (const float2*)h->hist.ptr(), (float2*)h->hist.buf[h->hist.cur ^ 1],
                            h->hist.H, (const float2*)in_dev, count, h->part.total_out, (float2*)out_dev, s);
