@@ -942,8 +942,19 @@ qdsp_deemp* qdsp_deemp_create(float sampleRate, float tau) {
     return h;
 }
 void qdsp_deemp_destroy(qdsp_deemp* h) { delete h; }
+// the chunk-with-warm-up recurrences re-read input that a neighbouring chunk's thread overwrites when out aliases in
+static bool ranges_overlap(const void* a, const void* b, long long count, size_t elem) {
+    const char* pa = (const char*)a;
+    const char* pb = (const char*)b;
+    const size_t bytes = (size_t)count * elem;
+    return pa < pb + bytes && pb < pa + bytes;
+}
 long long qdsp_deemp_process(qdsp_deemp* h, const void* in_dev, void* out_dev, long long count, qdsp_stream_t s) {
     if (count < 0) return -1;
+    if (count > 0 && ranges_overlap(in_dev, out_dev, count, 8)) {
+        set_last_error("deemp_process: in and out must not overlap (chunked scan with warm-up re-reads the input)");
+        return -1;
+    }
     if (launch_deemp((const float2*)in_dev, (float2*)out_dev, count, h->alpha, h->st.p, nullptr, 0, as_stream(s)) != 0)
         return -1;
     return count;
@@ -1086,6 +1097,10 @@ void qdsp_costas_destroy(qdsp_costas* h) { delete h; }
 long long qdsp_costas_process(qdsp_costas* h, const void* in_dev, void* out_dev, long long count, qdsp_stream_t s) {
     if (count < 0) return -1;
     if (count == 0) return 0;
+    if (ranges_overlap(in_dev, out_dev, count, 8)) {
+        set_last_error("costas_process: in and out must not overlap (chunked scan with warm-up re-reads the input)");
+        return -1;
+    }
     if (h->scratch.reserve(costas_scratch_bytes(count, h->chunk)) != 0) return -1;
     if (launch_costas((const float2*)in_dev, (float2*)out_dev, count, h->order, h->alpha, h->beta, h->st.p, h->chunk,
                       h->warmup, h->scratch.p, h->scratch.cap, h->st.p + 4, as_stream(s)) != 0)

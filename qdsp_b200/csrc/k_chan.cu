@@ -40,7 +40,11 @@ struct ChanArgs {
 // SLICE < 0: run-time slice (blockIdx.z), the slice's 8 x DC taps are staged in shared memory and read with broadcast
 // loads -- one body for every slice, used when few channel groups run per GPU (the immediate-tap bodies of different
 // slices would otherwise be resident together and thrash the instruction cache: ncu `no_instructions` stalls).
-template <int DS, int DC, bool ROT, int SLICE, int NR = 1>
+// WTAB: the per-sample rotation is split as phase(r, c) = P_r * W_c with W_c = e^{j theta_ch c} read from a per-CTA
+// shared-memory table [pair][lane] (one 128-bit load per column pair, shared by the NR rows of a step) and P_r applied to
+// the row partials after the column loop: z = x * W_c costs 8 FMA-pipe cycles per pair instead of 16 for rotating with a
+// running phasor. NW warps (row segments) of a CTA share the W table and the staged taps.
+template <int DS, int DC, bool ROT, int SLICE, int NR = 1, bool WTAB = false, int NW = 1>
 __device__ __forceinline__ void chan_body(const ChanArgs& ca) {
     constexpr int PAIRS = DC / 2;
     constexpr int RS = 4;                       // rows per ring stage (a multiple of NR)
@@ -51,13 +55,18 @@ __device__ __forceinline__ void chan_body(const ChanArgs& ca) {
     static_assert(DC % 4 == 0 && DS % DC == 0, "slice geometry");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const DecimArgs& a = ca.a;
-    const int lane = threadIdx.x;
-    const int seg = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int seg = blockIdx.x * NW + warp;
     const int slice = SLICE >= 0 ? SLICE : (int)blockIdx.z;
     const int b = blockIdx.y / ca.groups, group = blockIdx.y - b * ca.groups;
     const BlkInfo bi = a.part.get(b);
     const int k0 = seg * ca.seg_rows;
-    if (k0 >= bi.out_count) return;
+    // shared-memory carve-up: [CTA-wide: staged taps | W table][per warp: TMA ring | mbarriers]
+    constexpr uint32_t TAPS_BYTES = SLICE < 0 ? 8u * DC * 4u : 0u;
+    constexpr uint32_t WTAB_BYTES = WTAB ? (uint32_t)PAIRS * 32u * 16u : 0u;
+    constexpr uint32_t WARP_BYTES = NSTG * STAGE_BYTES + 64u;
+    unsigned char* smem_cta = smem_raw;
+    unsigned char* smem_warp = smem_raw + TAPS_BYTES + WTAB_BYTES + warp * WARP_BYTES;
     const int nout = bi.out_count - k0 < ca.seg_rows ? bi.out_count - k0 : ca.seg_rows;
     const int nrows = nout + 8;                                   // rows k0 .. k0 + nout - 1 + 8
     const int nstages = (nrows + RS - 1) / RS;
@@ -65,19 +74,30 @@ __device__ __forceinline__ void chan_body(const ChanArgs& ca) {
     const long long row0 = bi.in_start + (long long)k0 * DS - a.T - ca.pad + (long long)slice * DC;
     const int ch = group * 32 + lane;
     const bool ch_ok = ch < ca.nch;
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + NSTG * STAGE_BYTES);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_warp + NSTG * STAGE_BYTES);
     // taps of this slice: constant bank at immediate offsets, or shared memory [pair][q] (8 tap pairs = 64 bytes per pair)
     const float4* gt = c_chan_taps + (SLICE >= 0 ? SLICE : 0) * (DC / 4);
-    float4* gs = reinterpret_cast<float4*>(smem_raw + NSTG * STAGE_BYTES + 64);
+    float4* gs = reinterpret_cast<float4*>(smem_cta);
     if (SLICE < 0) {
         float2* gs2 = reinterpret_cast<float2*>(gs);
         const float* gsrc = ca.taps_dev;                      // [8][DS] floats (pad applied)
-        for (int e = lane; e < PAIRS * 8; e += 32) {
+        for (int e = threadIdx.x; e < PAIRS * 8; e += 32 * NW) {
             const int c = e >> 3, q = e & 7;
             const float* src = gsrc + (size_t)q * DS + (size_t)slice * DC + 2 * c;
             gs2[e] = make_float2(src[0], src[1]);
         }
     }
+    float4* wt = reinterpret_cast<float4*>(smem_cta + TAPS_BYTES);      // [PAIRS][32 lanes]: (W_2p, W_2p+1) of the lane's channel
+    if (WTAB && ROT) {
+        const uint64_t st = a.nco[(group * 32 + lane) < ca.nch ? group * 32 + lane : 0].step;
+        for (int pp = warp; pp < PAIRS; pp += NW) {
+            const float2 wa = phasor_from_turns(st * (uint64_t)(2 * pp));
+            const float2 wb = phasor_from_turns(st * (uint64_t)(2 * pp + 1));
+            wt[pp * 32 + lane] = make_float4(wa.x, wa.y, wb.x, wb.y);
+        }
+    }
+    if (NW > 1) __syncthreads();
+    if (k0 >= bi.out_count) return;
 
     uint64_t nco_step = 0, nco_ph0 = 0;
     if (ROT) {
@@ -94,7 +114,7 @@ __device__ __forceinline__ void chan_body(const ChanArgs& ca) {
     auto issue = [&](int st) {
         if (st >= nstages) return;
         const int slot = st % NSTG;
-        unsigned char* dst = smem_raw + slot * STAGE_BYTES;
+        unsigned char* dst = smem_warp + slot * STAGE_BYTES;
         const long long s0 = row0 + (long long)st * RS * DS;                    // first sample of the stage's first row
         const long long last_end = s0 + (long long)(RS - 1) * DS + DC;
         if (s0 >= 0 && last_end <= a.n_in) {
@@ -143,7 +163,7 @@ __device__ __forceinline__ void chan_body(const ChanArgs& ca) {
             float2 PR[NR], PI[NR];
 #pragma unroll
             for (int j = 0; j < NR; j++) {
-                xrow[j] = reinterpret_cast<const float4*>(smem_raw + slot * STAGE_BYTES + (rr + j) * ROW_BYTES);
+                xrow[j] = reinterpret_cast<const float4*>(smem_warp + slot * STAGE_BYTES + (rr + j) * ROW_BYTES);
                 PR[j] = make_float2(1.f, 1.f);
                 PI[j] = make_float2(0.f, 0.f);
                 if (ROT) {
@@ -160,9 +180,17 @@ __device__ __forceinline__ void chan_body(const ChanArgs& ca) {
             for (int c = 0; c < PAIRS; c++) {
                 float2 RE[NR], IM[NR];
 #pragma unroll
+                float4 w4 = make_float4(1.f, 0.f, 1.f, 0.f);
+                if (ROT && WTAB) w4 = wt[c * 32 + lane];
+#pragma unroll
                 for (int j = 0; j < NR; j++) {
                     const float4 v = xrow[j][c];
-                    if (ROT) {
+                    if (ROT && WTAB) {
+                        RE[j].x = fmaf(v.x, w4.x, -(v.y * w4.y));
+                        IM[j].x = fmaf(v.x, w4.y, v.y * w4.x);
+                        RE[j].y = fmaf(v.z, w4.z, -(v.w * w4.w));
+                        IM[j].y = fmaf(v.z, w4.w, v.w * w4.z);
+                    } else if (ROT) {
                         RE[j].x = fmaf(v.x, PR[j].x, -(v.y * PI[j].x));
                         IM[j].x = fmaf(v.x, PI[j].x, v.y * PR[j].x);
                         RE[j].y = fmaf(v.z, PR[j].y, -(v.w * PI[j].y));
@@ -211,12 +239,18 @@ __device__ __forceinline__ void chan_body(const ChanArgs& ca) {
             // outputs in flight: output (row - q) takes that row's S_q
 #pragma unroll
             for (int j = 0; j < NR; j++) {
-                const float2 s8 = make_float2(sRe[j].x + sRe[j].y, sIm[j].x + sIm[j].y);
+                // WTAB: the row's phasor (exact, at the slice's first column) multiplies the row partials here
+                const float2 Pj = make_float2(PR[j].x, PI[j].x);
+                auto fin = [&](float2 re2, float2 im2) {
+                    float2 v = make_float2(re2.x + re2.y, im2.x + im2.y);
+                    if (ROT && WTAB) v = cmul(v, Pj);
+                    return v;
+                };
+                const float2 s8 = fin(sRe[j], sIm[j]);
                 const float2 y = __fadd2_rn(O[7], s8);                 // output row - 8 is complete
 #pragma unroll
-                for (int q = 7; q >= 1; q--)
-                    O[q] = __fadd2_rn(O[q - 1], make_float2(aRe[j][q].x + aRe[j][q].y, aIm[j][q].x + aIm[j][q].y));
-                O[0] = make_float2(aRe[j][0].x + aRe[j][0].y, aIm[j][0].x + aIm[j][0].y);
+                for (int q = 7; q >= 1; q--) O[q] = __fadd2_rn(O[q - 1], fin(aRe[j][q], aIm[j][q]));
+                O[0] = fin(aRe[j][0], aIm[j][0]);
                 const int k = r + j - 8;
                 if (k >= 0 && k < nout && ch_ok) plane[k] = y;
             }
@@ -242,6 +276,10 @@ __global__ void __launch_bounds__(32) chan_kernel(const __grid_constant__ ChanAr
 template <int DS, int DC, bool ROT, int NRT>
 __global__ void __launch_bounds__(32) chan_smemtaps_kernel(const __grid_constant__ ChanArgs ca) {
     chan_body<DS, DC, ROT, -1, NRT>(ca);
+}
+template <int DS, int DC, int NRT, int NW>
+__global__ void __launch_bounds__(32 * NW) chan_wtab_kernel(const __grid_constant__ ChanArgs ca) {
+    chan_body<DS, DC, true, -1, NRT, true, NW>(ca);
 }
 
 // ---- host side -------------------------------------------------------------------------------------
@@ -316,7 +354,21 @@ static int launch_chan_t(DecimPlan* plan, const float* taps_host, const float2* 
     const bool smemtaps = smt_env >= 0 ? smt_env != 0 : ca.groups < 4;
     constexpr size_t smem = 4 * 4 * DC * 8 + 64 + 8 * DC * 4 + 64;
     static const int nr_env = getenv("QDSP_CHAN_NR") ? atoi(getenv("QDSP_CHAN_NR")) : 2;
-    if (rot && smemtaps && nr_env == 2) {
+    static const int wtab_env = getenv("QDSP_CHAN_WTAB") ? atoi(getenv("QDSP_CHAN_WTAB")) : 0;
+    if (rot && wtab_env != 0) {
+        constexpr int NW = 4;
+        constexpr size_t smem_w = 8 * DC * 4 + (DC / 2) * 32 * 16 + NW * (4 * 4 * DC * 8 + 64) + 64;
+        dim3 gridw((grid.x + NW - 1) / NW, grid.y, grid.z);
+        if (wtab_env == 2) {
+            auto kern = chan_wtab_kernel<DS, DC, 2, NW>;
+            QDSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+            kern<<<gridw, 32 * NW, smem_w, s>>>(ca);
+        } else {
+            auto kern = chan_wtab_kernel<DS, DC, 1, NW>;
+            QDSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+            kern<<<gridw, 32 * NW, smem_w, s>>>(ca);
+        }
+    } else if (rot && smemtaps && nr_env == 2) {
         auto kern = chan_smemtaps_kernel<DS, DC, true, 2>;
         QDSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, 32, smem, s>>>(ca);
