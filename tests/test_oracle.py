@@ -111,3 +111,68 @@ def test_nco_drift_attribution(port):
     y_f64, _ = port.rotator_f64(x, inc)
     drift = np.angle(y_f32[-1] * np.conj(y_f64[-1]))
     assert 1e-3 < abs(drift) < 1e-1
+
+
+# ---- round 2: the oracle pieces behind the full-size window checks and the NCO replay -----------------------------
+def test_window_oracle_equals_full_stream_oracle(port):
+    # oracle/windows.py recomputes windows of a long stream from scratch (zero history + pre-roll, float64 rotator started
+    # at the window's absolute phase): after the start-up outputs it must equal the whole-stream oracle to float rounding
+    from oracle import windows
+    from qdsp_b200 import synth
+
+    block, n = 80000, 80000 * 6 + 4000
+    x = synth.cfg2_input(0, n)
+    full, oc = port.vfo_fm(250e3, 2.4e6, 48e3, 48e3, 5e3, x, block, nco_f64=True)
+    seams = [block, 3 * block, 6 * block]
+    centres = windows.pick_windows(n, block, 5, 16384, seams)
+    worst, cnt = windows.check_vfofm_windows(lambda lo, hi: x[lo:hi], full, n, block, centres, 16384, 250e3, 2.4e6, 48e3, 48e3,
+                                             5e3, 50, 401)
+    # (the two evaluate the float64 phase by different double-precision routes: a rare 1-ulp difference in a mixed sample)
+    assert cnt > 2000 and worst <= 1e-6, worst
+    # a wrong output somewhere inside a window is caught
+    bad = full.copy()
+    bad[(3 * block) // 50 + 7] += 1e-3
+    worst_bad, _ = windows.check_vfofm_windows(lambda lo, hi: x[lo:hi], bad, n, block, centres, 16384, 250e3, 2.4e6, 48e3, 48e3,
+                                               5e3, 50, 401)
+    assert worst_bad > 5e-4
+
+
+def test_fir_window_oracle(port):
+    from oracle import windows
+    from qdsp_b200 import synth
+
+    n = 60000
+    x = synth.uniform_cf32(3, 0, n)
+    taps = port.blackman_taps(100e3, 4 * 2.4e6 / 4095, 2.4e6)
+    y = port.fir_cf32(taps, x)
+    centres = windows.pick_windows(n, 1 << 14, 3, 2048, [30000])
+    rel, mx, cnt = windows.check_fir_windows(lambda lo, hi: x[lo:hi], y, None, n, taps, centres, 2048)
+    assert rel == 0.0 and cnt > 6000
+
+
+def test_rotator_checkpoints_reproduce_the_recursive_rotator(port):
+    # the per-512-sample phase states handed to qdsp_vfofm_process_replay: replaying the float recursion from each
+    # checkpoint must give the reference rotator's output bit for bit (this is what xlator_replay_kernel does on the GPU)
+    from qdsp_b200 import synth
+
+    sizes = [1000, 512, 3, 0, 4096, 777]
+    n = sum(sizes)
+    x = synth.uniform_cf32(2, 0, n)
+    inc = port.xlator_phase_delta(2.4e6, -250e3)
+    want, end = port.rotator(x, inc, 1 + 0j, sizes)
+    ck, end2 = port.rotator_checkpoints(inc, sizes)
+    assert end == end2 and len(ck) == sum((s + 511) // 512 for s in sizes)
+    got = np.empty(n, np.complex64)
+    f32 = np.float32
+    ir, ii = f32(inc.real), f32(inc.imag)
+    k, off = 0, 0
+    for s in sizes:
+        for r0 in range(0, s, 512):
+            pr, pi = f32(ck[k].real), f32(ck[k].imag)
+            k += 1
+            for j in range(r0, min(r0 + 512, s)):
+                xr, xi = f32(x[off + j].real), f32(x[off + j].imag)
+                got[off + j] = complex(f32(f32(xr * pr) - f32(xi * pi)), f32(f32(xr * pi) + f32(xi * pr)))
+                pr, pi = f32(f32(pr * ir) - f32(pi * ii)), f32(f32(pr * ii) + f32(pi * ir))
+        off += s
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
