@@ -1,6 +1,7 @@
 // qdsp_b200/csrc/api.cu — the C ABI (include/qdsp_b200.h): opaque handles, state, dispatch.
 // No compute happens on the host; every process call enqueues sm_100a kernels on the caller's stream.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <new>
 #include <vector>
@@ -1086,6 +1087,8 @@ qdsp_costas* qdsp_costas_create(int order, float loopBandwidth) {
     const float den = (float)(1.0 + 2.0 * damp * loopBandwidth + loopBandwidth * loopBandwidth);
     h->alpha = (4 * damp * loopBandwidth) / den;
     h->beta = (4 * loopBandwidth * loopBandwidth) / den;
+    if (const char* e = getenv("QDSP_COSTAS_CHUNK")) h->chunk = atoi(e) >= 16 ? atoi(e) / 16 * 16 : h->chunk;      // A/B switches
+    if (const char* e = getenv("QDSP_COSTAS_WARMUP")) h->warmup = atoi(e) >= 0 ? atoi(e) / 16 * 16 : h->warmup;
     const float init[5] = {0.0f, 0.0f, 1.0f, 0.0f, 0.0f};
     if (h->st.init(5, init) != 0) {
         delete h;

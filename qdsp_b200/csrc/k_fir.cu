@@ -16,8 +16,7 @@
 #include <stdlib.h>
 #include <new>
 #include <vector>
-#include "internal.cuh"
-#include "kernels.cuh"
+#include "decim_common.cuh"
 
 namespace qdsp {
 
@@ -98,8 +97,31 @@ fir_dense_kernel(VStream<float2> xs, long long count, const float2* __restrict__
     const long long B = n_t - (T - 1);                                // sample index of quad 0, element 0
 
     // ---- staging: taps, then the tile's window as (re, re, im, im) quads --------------------------
+    // interior tiles whose window starts on an even sample: ONE TMA bulk copy drops the raw interleaved window
+    // (re0, im0, re1, im1 per 16 bytes) into the quad array -- the whole tile in flight at once, no staging registers --
+    // and every thread then swaps the two middle floats of its quads in place
+    __shared__ uint64_t s_mbar;
+    const bool tma_tile = (B & 1) == 0 && (reinterpret_cast<uintptr_t>(xs.in) & 15) == 0 && B >= 0 &&
+                          B + 2 * (long long)npairs <= count;
+    if (tma_tile) {
+        if (t == 0) {
+            mbar_init(&s_mbar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (t == 0) {
+            mbar_arrive_expect_tx(&s_mbar, (uint32_t)npairs * 16u);
+            tma_bulk_g2s(sq, xs.in + B, (uint32_t)npairs * 16u, &s_mbar);
+        }
+    }
     for (int i = t; i < 2 * U; i += NT) st[i] = taps[i];
-    if ((B & 1) == 0 && (reinterpret_cast<uintptr_t>(xs.in) & 15) == 0) {
+    if (tma_tile) {
+        mbar_wait(&s_mbar, 0);
+        for (int q = t; q < npairs; q += NT) {
+            const float4 a = sq[q];
+            sq[q] = make_float4(a.x, a.z, a.y, a.w);
+        }
+    } else if ((B & 1) == 0 && (reinterpret_cast<uintptr_t>(xs.in) & 15) == 0) {
         // the window starts on an even sample (odd tap counts): one 128-bit load -> one quad, 4 in flight per thread
         for (int q0 = t; q0 < npairs; q0 += 4 * NT) {
             float4 a[4];
