@@ -924,6 +924,7 @@ struct qdsp_costas {
     // measured on B200 (2^26 QPSK samples, tools/_costas_sweep.py): (4096, 4096) 38 GS/s, (2048, 2048) 49 GS/s with the same
     // 4e-6 error against the sequential loop; 1536 warm-up samples: 53 GS/s but 2e-5; 1024: 1e-3 (not merged)
     int chunk = 2048, warmup = 2048;
+    bool chunk_user = false;   // set_chunking() / environment: keep; otherwise long calls use 4096-sample chunks
     DevState st;   // [4] state + [1] residual
     Scratch scratch;
 };
@@ -1087,7 +1088,10 @@ qdsp_costas* qdsp_costas_create(int order, float loopBandwidth) {
     const float den = (float)(1.0 + 2.0 * damp * loopBandwidth + loopBandwidth * loopBandwidth);
     h->alpha = (4 * damp * loopBandwidth) / den;
     h->beta = (4 * loopBandwidth * loopBandwidth) / den;
-    if (const char* e = getenv("QDSP_COSTAS_CHUNK")) h->chunk = atoi(e) >= 16 ? atoi(e) / 16 * 16 : h->chunk;      // A/B switches
+    if (const char* e = getenv("QDSP_COSTAS_CHUNK")) {      // A/B switches
+        h->chunk = atoi(e) >= 16 ? atoi(e) / 16 * 16 : h->chunk;
+        h->chunk_user = true;
+    }
     if (const char* e = getenv("QDSP_COSTAS_WARMUP")) h->warmup = atoi(e) >= 0 ? atoi(e) / 16 * 16 : h->warmup;
     const float init[5] = {0.0f, 0.0f, 1.0f, 0.0f, 0.0f};
     if (h->st.init(5, init) != 0) {
@@ -1104,8 +1108,11 @@ long long qdsp_costas_process(qdsp_costas* h, const void* in_dev, void* out_dev,
         set_last_error("costas_process: in and out must not overlap (chunked scan with warm-up re-reads the input)");
         return -1;
     }
-    if (h->scratch.reserve(costas_scratch_bytes(count, h->chunk)) != 0) return -1;
-    if (launch_costas((const float2*)in_dev, (float2*)out_dev, count, h->order, h->alpha, h->beta, h->st.p, h->chunk,
+    // the work is (1 + warmup / chunk) x the sequential loop's: with >= 32768 chunks of 4096 samples the machine is still full
+    // (B200, 2^28 QPSK samples, GS/s: chunk 2048: 95, 3072: 95, 4096: 110, 8192: 103; warm-up 2048 throughout)
+    const int chunk = (!h->chunk_user && count >= (1ll << 27)) ? 4096 : h->chunk;
+    if (h->scratch.reserve(costas_scratch_bytes(count, chunk)) != 0) return -1;
+    if (launch_costas((const float2*)in_dev, (float2*)out_dev, count, h->order, h->alpha, h->beta, h->st.p, chunk,
                       h->warmup, h->scratch.p, h->scratch.cap, h->st.p + 4, as_stream(s)) != 0)
         return -1;
     return count;
@@ -1119,6 +1126,7 @@ int qdsp_costas_set_chunking(qdsp_costas* h, int chunk, int warmup) {
     }
     h->chunk = chunk;
     h->warmup = warmup;
+    h->chunk_user = true;
     return 0;
 }
 float qdsp_costas_last_residual(qdsp_costas* h) {
