@@ -277,10 +277,6 @@ template <int DS, int DC, bool ROT, int NRT>
 __global__ void __launch_bounds__(32) chan_smemtaps_kernel(const __grid_constant__ ChanArgs ca) {
     chan_body<DS, DC, ROT, -1, NRT>(ca);
 }
-template <int DS, int DC, int NRT, int NW>
-__global__ void __launch_bounds__(32 * NW) chan_wtab_kernel(const __grid_constant__ ChanArgs ca) {
-    chan_body<DS, DC, true, -1, NRT, true, NW>(ca);
-}
 
 // ---- host side -------------------------------------------------------------------------------------
 bool chan_supported(const DecimPlan* plan) {
@@ -354,21 +350,7 @@ static int launch_chan_t(DecimPlan* plan, const float* taps_host, const float2* 
     const bool smemtaps = smt_env >= 0 ? smt_env != 0 : ca.groups < 4;
     constexpr size_t smem = 4 * 4 * DC * 8 + 64 + 8 * DC * 4 + 64;
     static const int nr_env = getenv("QDSP_CHAN_NR") ? atoi(getenv("QDSP_CHAN_NR")) : 2;
-    static const int wtab_env = getenv("QDSP_CHAN_WTAB") ? atoi(getenv("QDSP_CHAN_WTAB")) : 0;
-    if (rot && wtab_env != 0) {
-        constexpr int NW = 4;
-        constexpr size_t smem_w = 8 * DC * 4 + (DC / 2) * 32 * 16 + NW * (4 * 4 * DC * 8 + 64) + 64;
-        dim3 gridw((grid.x + NW - 1) / NW, grid.y, grid.z);
-        if (wtab_env == 2) {
-            auto kern = chan_wtab_kernel<DS, DC, 2, NW>;
-            QDSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
-            kern<<<gridw, 32 * NW, smem_w, s>>>(ca);
-        } else {
-            auto kern = chan_wtab_kernel<DS, DC, 1, NW>;
-            QDSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
-            kern<<<gridw, 32 * NW, smem_w, s>>>(ca);
-        }
-    } else if (rot && smemtaps && nr_env == 2) {
+    if (rot && smemtaps && nr_env == 2) {
         auto kern = chan_smemtaps_kernel<DS, DC, true, 2>;
         QDSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, 32, smem, s>>>(ca);
