@@ -40,7 +40,8 @@ struct ChanArgs {
 // SLICE < 0: run-time slice (blockIdx.z), the slice's 8 x DC taps are staged in shared memory and read with broadcast
 // loads -- one body for every slice, used when few channel groups run per GPU (the immediate-tap bodies of different
 // slices would otherwise be resident together and thrash the instruction cache: ncu `no_instructions` stalls).
-// WTAB: the per-sample rotation is split as phase(r, c) = P_r * W_c with W_c = e^{j theta_ch c} read from a per-CTA
+// WTAB (experimental, measured slower, not instantiated -- DESIGN.md 6.0b): the per-sample rotation is split as
+// phase(r, c) = P_r * W_c with W_c = e^{j theta_ch c} read from a per-CTA
 // shared-memory table [pair][lane] (one 128-bit load per column pair, shared by the NR rows of a step) and P_r applied to
 // the row partials after the column loop: z = x * W_c costs 8 FMA-pipe cycles per pair instead of 16 for rotating with a
 // running phasor. NW warps (row segments) of a CTA share the W table and the staged taps.

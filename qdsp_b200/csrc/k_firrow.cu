@@ -225,7 +225,7 @@ bool firrow_supported(int T, int D) {
 int launch_firrow(const float* taps_host, int T, int D, const float2* hist, float2* hist_next, int H, const float2* in,
                   long long count, long long n_out, float2* out, cudaStream_t s) {
     if (n_out <= 0) return 0;
-    constexpr int DROW = 28, Q = 6, NPH = 7, NSTG = 3;
+    constexpr int DROW = 28, Q = 6, NPH = 7;
     if (!firrow_supported(T, D) || (reinterpret_cast<uintptr_t>(in) & 15) != 0) {
         set_last_error("firrow: unsupported geometry");
         return -1;
@@ -253,10 +253,20 @@ int launch_firrow(const float* taps_host, int T, int D, const float2* hist, floa
     const long long nrows = (n_out + NPH - 1) / NPH;
     const int rows_per_tile = 32 * fa.nstep - (Q - 1);
     const long long tiles = (nrows + rows_per_tile - 1) / rows_per_tile;
-    constexpr size_t smem = NSTG * 32 * (DROW * 8) + NSTG * 8 + 16;
-    auto kern = fir_rowphase_kernel<4, DROW, Q, 127, PAD, NSTG>;
-    QDSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)tiles, 32, smem, s>>>(fa);
+    static const int nstg_env = getenv("QDSP_FIRROW_NSTG") ? atoi(getenv("QDSP_FIRROW_NSTG")) : 2;   // 2 slots: 15 warps per SM (315 GS/s); 3 slots: 10 (310)
+    if (nstg_env == 2) {
+        constexpr int NSTG = 2;
+        constexpr size_t smem = NSTG * 32 * (DROW * 8) + NSTG * 8 + 16;
+        auto kern = fir_rowphase_kernel<4, DROW, Q, 127, PAD, NSTG>;
+        QDSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)tiles, 32, smem, s>>>(fa);
+    } else {
+        constexpr int NSTG = 3;
+        constexpr size_t smem = NSTG * 32 * (DROW * 8) + NSTG * 8 + 16;
+        auto kern = fir_rowphase_kernel<4, DROW, Q, 127, PAD, NSTG>;
+        QDSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)tiles, 32, smem, s>>>(fa);
+    }
     QDSP_LAUNCH_OK();
     return 0;
 }
