@@ -40,12 +40,7 @@ struct ChanArgs {
 // SLICE < 0: run-time slice (blockIdx.z), the slice's 8 x DC taps are staged in shared memory and read with broadcast
 // loads -- one body for every slice, used when few channel groups run per GPU (the immediate-tap bodies of different
 // slices would otherwise be resident together and thrash the instruction cache: ncu `no_instructions` stalls).
-// WTAB (experimental, measured slower, not instantiated -- DESIGN.md 6.0b): the per-sample rotation is split as
-// phase(r, c) = P_r * W_c with W_c = e^{j theta_ch c} read from a per-CTA
-// shared-memory table [pair][lane] (one 128-bit load per column pair, shared by the NR rows of a step) and P_r applied to
-// the row partials after the column loop: z = x * W_c costs 8 FMA-pipe cycles per pair instead of 16 for rotating with a
-// running phasor. NW warps (row segments) of a CTA share the W table and the staged taps.
-template <int DS, int DC, bool ROT, int SLICE, int NR = 1, bool WTAB = false, int NW = 1>
+template <int DS, int DC, bool ROT, int SLICE, int NR = 1>
 __device__ __forceinline__ void chan_body(const ChanArgs& ca) {
     constexpr int PAIRS = DC / 2;
     constexpr int RS = 4;                       // rows per ring stage (a multiple of NR)
@@ -56,18 +51,16 @@ __device__ __forceinline__ void chan_body(const ChanArgs& ca) {
     static_assert(DC % 4 == 0 && DS % DC == 0, "slice geometry");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const DecimArgs& a = ca.a;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int seg = blockIdx.x * NW + warp;
+    const int lane = threadIdx.x;
+    const int seg = blockIdx.x;
     const int slice = SLICE >= 0 ? SLICE : (int)blockIdx.z;
     const int b = blockIdx.y / ca.groups, group = blockIdx.y - b * ca.groups;
     const BlkInfo bi = a.part.get(b);
     const int k0 = seg * ca.seg_rows;
-    // shared-memory carve-up: [CTA-wide: staged taps | W table][per warp: TMA ring | mbarriers]
+    // shared-memory carve-up: [staged taps (shared-memory-tap variant)][TMA ring | mbarriers]
     constexpr uint32_t TAPS_BYTES = SLICE < 0 ? 8u * DC * 4u : 0u;
-    constexpr uint32_t WTAB_BYTES = WTAB ? (uint32_t)PAIRS * 32u * 16u : 0u;
-    constexpr uint32_t WARP_BYTES = NSTG * STAGE_BYTES + 64u;
     unsigned char* smem_cta = smem_raw;
-    unsigned char* smem_warp = smem_raw + TAPS_BYTES + WTAB_BYTES + warp * WARP_BYTES;
+    unsigned char* smem_warp = smem_raw + TAPS_BYTES;
     const int nout = bi.out_count - k0 < ca.seg_rows ? bi.out_count - k0 : ca.seg_rows;
     const int nrows = nout + 8;                                   // rows k0 .. k0 + nout - 1 + 8
     const int nstages = (nrows + RS - 1) / RS;
@@ -82,22 +75,13 @@ __device__ __forceinline__ void chan_body(const ChanArgs& ca) {
     if (SLICE < 0) {
         float2* gs2 = reinterpret_cast<float2*>(gs);
         const float* gsrc = ca.taps_dev;                      // [8][DS] floats (pad applied)
-        for (int e = threadIdx.x; e < PAIRS * 8; e += 32 * NW) {
+        for (int e = lane; e < PAIRS * 8; e += 32) {
             const int c = e >> 3, q = e & 7;
             const float* src = gsrc + (size_t)q * DS + (size_t)slice * DC + 2 * c;
             gs2[e] = make_float2(src[0], src[1]);
         }
     }
-    float4* wt = reinterpret_cast<float4*>(smem_cta + TAPS_BYTES);      // [PAIRS][32 lanes]: (W_2p, W_2p+1) of the lane's channel
-    if (WTAB && ROT) {
-        const uint64_t st = a.nco[(group * 32 + lane) < ca.nch ? group * 32 + lane : 0].step;
-        for (int pp = warp; pp < PAIRS; pp += NW) {
-            const float2 wa = phasor_from_turns(st * (uint64_t)(2 * pp));
-            const float2 wb = phasor_from_turns(st * (uint64_t)(2 * pp + 1));
-            wt[pp * 32 + lane] = make_float4(wa.x, wa.y, wb.x, wb.y);
-        }
-    }
-    if (NW > 1) __syncthreads();
+    __syncwarp();
     if (k0 >= bi.out_count) return;
 
     uint64_t nco_step = 0, nco_ph0 = 0;
@@ -181,17 +165,10 @@ __device__ __forceinline__ void chan_body(const ChanArgs& ca) {
             for (int c = 0; c < PAIRS; c++) {
                 float2 RE[NR], IM[NR];
 #pragma unroll
-                float4 w4 = make_float4(1.f, 0.f, 1.f, 0.f);
-                if (ROT && WTAB) w4 = wt[c * 32 + lane];
 #pragma unroll
                 for (int j = 0; j < NR; j++) {
                     const float4 v = xrow[j][c];
-                    if (ROT && WTAB) {
-                        RE[j].x = fmaf(v.x, w4.x, -(v.y * w4.y));
-                        IM[j].x = fmaf(v.x, w4.y, v.y * w4.x);
-                        RE[j].y = fmaf(v.z, w4.z, -(v.w * w4.w));
-                        IM[j].y = fmaf(v.z, w4.w, v.w * w4.z);
-                    } else if (ROT) {
+                    if (ROT) {
                         RE[j].x = fmaf(v.x, PR[j].x, -(v.y * PI[j].x));
                         IM[j].x = fmaf(v.x, PI[j].x, v.y * PR[j].x);
                         RE[j].y = fmaf(v.z, PR[j].y, -(v.w * PI[j].y));
@@ -240,13 +217,7 @@ __device__ __forceinline__ void chan_body(const ChanArgs& ca) {
             // outputs in flight: output (row - q) takes that row's S_q
 #pragma unroll
             for (int j = 0; j < NR; j++) {
-                // WTAB: the row's phasor (exact, at the slice's first column) multiplies the row partials here
-                const float2 Pj = make_float2(PR[j].x, PI[j].x);
-                auto fin = [&](float2 re2, float2 im2) {
-                    float2 v = make_float2(re2.x + re2.y, im2.x + im2.y);
-                    if (ROT && WTAB) v = cmul(v, Pj);
-                    return v;
-                };
+                auto fin = [&](float2 re2, float2 im2) { return make_float2(re2.x + re2.y, im2.x + im2.y); };
                 const float2 s8 = fin(sRe[j], sIm[j]);
                 const float2 y = __fadd2_rn(O[7], s8);                 // output row - 8 is complete
 #pragma unroll
