@@ -177,3 +177,24 @@ def test_cpp_graph_matches_oracle(qlib, tmp_path, mode):
     assert np.abs(y[16:] - ref[16:]).max() <= 1e-4
     ref32, _ = loader.port().vfo_fm(250e3, 2.4e6, 48e3, 48e3, 5e3, x[:2 * blk], blk)
     assert np.abs(y[16:len(ref32)] - ref32[16:]).max() <= 1e-4
+
+
+@pytest.mark.gpu
+def test_cpp_host_edges_graph_matches_oracle(qlib, tmp_path):
+    # HandlerSource (callback fills writeBuf) -> Splitter -> {fused VFO+FM -> FileSink<float>, FrequencyXlator -> NullSink}
+    from oracle import loader
+    from qdsp_b200 import synth
+
+    exe = tmp_path / "edges_chain"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "edges_chain.cpp"),
+                           "-L" + os.path.join(ROOT, "qdsp_b200"), "-lqdsp_b200", "-lpthread",
+                           "-Wl,-rpath," + os.path.join(ROOT, "qdsp_b200"), "-o", str(exe)])
+    n, blk = 819200, 81920
+    x = synth.cfg2_input(0, n)
+    fin, fout = tmp_path / "in.cf32", tmp_path / "out.f32"
+    x.tofile(fin)
+    subprocess.check_call([str(exe), str(fin), str(fout), str(blk)], timeout=120)
+    y = np.fromfile(fout, np.float32)
+    ref, _ = loader.port().vfo_fm(250e3, 2.4e6, 48e3, 48e3, 5e3, x, blk, nco_f64=True)
+    assert y.shape == ref.shape
+    assert np.abs(y[16:] - ref[16:]).max() <= 1e-4
