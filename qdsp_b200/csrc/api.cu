@@ -479,6 +479,7 @@ struct qdsp_channelizer {
     History hist;                // raw (untranslated) input tail, shared by all channels
     Partition part;
     DecimPlan* plan = nullptr;
+    ChanFftPlan* fftplan = nullptr;   // uniform 256-channel comb: FFT polyphase channelizer (k_chanfft.cu)
     DevState demod;              // [2][nch] ping-pong
     int cur = 0;
     long long abs_pos = 0;       // absolute index of the next input sample (NCO closed form)
@@ -532,6 +533,11 @@ struct qdsp_channelizer {
         std::vector<float> z(2 * nch, 0.0f);
         if (demod.init(2 * nch, z.data()) != 0) return -1;
         if (decim_plan_supported(T, interp, decim)) plan = decim_plan_create(taps.data(), T, decim);
+        {
+            std::vector<uint64_t> steps(nch);
+            for (int c = 0; c < nch; c++) steps[c] = nco[c].step;
+            fftplan = chanfft_plan_create(taps.data(), T, interp, decim, nch, steps.data());   // nullptr unless a uniform comb
+        }
         return 0;
     }
     long long process(const void* in_dev, float* audio, void* iq, long long out_stride, long long count,
@@ -561,7 +567,11 @@ struct qdsp_channelizer {
         }
         bool hist_folded = false;
         int rpad = -1;
-        if (plan && variant != 1 && nch == 1 && rowlane_supported(plan) && (reinterpret_cast<uintptr_t>(in_dev) & 15) == 0 &&
+        if (fftplan && variant == 0 && !iq && chanfft_usable(fftplan, part, in_dev)) {
+            // all 256 channels from one pass of column filters + two 256-point FFTs per output row
+            rc = launch_chanfft(fftplan, (const float2*)hist.ptr(), hist.H, (const float2*)in_dev, part, nco[0].step, nco[0].phase,
+                                abs_pos, phasor_speed, din, dout, audio, out_stride, s);
+        } else if (plan && variant != 1 && nch == 1 && rowlane_supported(plan) && (reinterpret_cast<uintptr_t>(in_dev) & 15) == 0 &&
             part.max_out > 0 && (rpad = rowlane_uniform_pad(part, T)) >= 0) {
             // row-per-lane kernel; the history advance (resampling.h:129) is folded into its first CTA
             const NcoDev nh{nco[0].phase, nco[0].step};
@@ -593,6 +603,7 @@ struct qdsp_channelizer {
         if (nco_dev) cudaFree(nco_dev);
         if (phases_dev) cudaFree(phases_dev);
         if (plan) decim_plan_destroy(plan);
+        if (fftplan) chanfft_plan_destroy(fftplan);
         if (plan_replay) decim_plan_destroy(plan_replay);
         hist.release();
         hist_mixed.release();

@@ -68,6 +68,15 @@ int launch_decim_finish(const float2* ypart, long long ypart_stride, int nslices
                         float phasor_speed, const float* demod_in, float* demod_out, float2* out_iq, float* audio,
                         long long out_stride, int nch, cudaStream_t s);
 
+// ---- k_chanfft.cu: FFT polyphase channelizer (256 channels on a uniform fs/256 comb, decimation 1280) ---------------
+struct ChanFftPlan;
+ChanFftPlan* chanfft_plan_create(const float* taps, int T, int interp, int decim, int nch, const uint64_t* nco_steps);
+void chanfft_plan_destroy(ChanFftPlan* p);
+bool chanfft_usable(const ChanFftPlan* p, const Partition& part, const void* in);
+int launch_chanfft(ChanFftPlan* plan, const float2* hist, int H, const float2* in, const Partition& part, uint64_t beta_step,
+                   uint64_t beta_ph0, long long abs0, float phasor_speed, const float* demod_in, float* demod_out, float* audio,
+                   long long out_stride, cudaStream_t s);
+
 // ---- k_fir.cu: register-blocked dense FIR (cf32, D = 1) -----------------------------------------
 struct FirPlan;
 FirPlan* fir_plan_create(const float* taps, int T);
