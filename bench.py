@@ -17,8 +17,10 @@ clocks sample and oracle check:
   cfg1a / cfg1b   127-tap FIR, and FIR + decimate-by-4, 2^24 samples                     (N = 1 only)
   cfg3            4095-tap FIR on 2^30 samples, TIME-SHARDED over the N ranks; the (taps-1)-sample halo is read by the
                   FIR kernel straight from the neighbour's memory over NVLink (CUDA IPC peer mapping)   (strong scaling)
-  cfg4            256-channel channelizer off one 61.44 MS/s stream of 2^26 samples, channels PARTITIONED over the N
-                  ranks, no collective                                                                   (strong scaling)
+  cfg4            256-channel channelizer off a 61.44 MS/s stream, FFT polyphase form (the default path for this geometry): all
+                  256 channels on every GPU, the stream TIME-SHARDED (2^26 samples + lead-in per rank), no collective  (weak scaling)
+  cfg4_direct     the same channelizer in direct form (the reference's algorithm), 2^26 samples, channels PARTITIONED over
+                  the N ranks, no collective                                                             (strong scaling)
   cfg5            recurrent blocks (de-emphasis, ComplexAGC, AGC, FeedForwardAGC, Costas) on 2^28 samples (N = 1 only)
 """
 import argparse
@@ -615,6 +617,82 @@ def run_cfg3(cx: Ctx, fp32_peak):
 
 # ---- config 4: 256-channel channelizer, channels partitioned over the ranks -----------------------------------
 def run_cfg4(cx: Ctx, fp32_peak):
+    """Two records. `cfg4`: the product's default path for this geometry -- the FFT polyphase channelizer (k_chanfft.cu), all
+    256 channels on every GPU, the STREAM time-sharded at N > 1 (weak: 2^26 samples per GPU, each shard fed 16 output rows of
+    lead-in it drops; no collective). `cfg4_direct`: the direct form (every channel its own VFO, the reference's algorithm
+    unchanged), channels partitioned over the GPUs (strong) -- round 1's record, kept for continuity and the FP32 roofline."""
+    out = {"cfg4_direct": _cfg4_direct(cx, fp32_peak)}
+    if not (cx.args.cfg4_world and cx.world == 1):
+        out["cfg4"] = _cfg4_fft(cx)
+    return out
+
+
+def _cfg4_fft(cx: Ctx):
+    from oracle import windows
+    from qdsp_b200 import blocks as B, synth
+
+    L, lib = cx.L, cx.lib
+    n, nch = cx.args.n4, 256
+    fs, spacing, D, blk = 61_440_000, 240_000, 1280, 819200
+    lead = 16 * D if cx.rank > 0 else 0          # >= history (10 240) + one row for the demodulator's previous angle
+    g0 = cx.rank * n - lead                      # stream position of this rank's first local sample
+    offs = synth.cfg4_offsets(nch, spacing)
+    x = B.DevBuf((n + lead) * 8)
+    lib.check(L.qdsp_synth_comb_cf32(x.ptr, g0, n + lead, fs, nch, spacing, 5e3, 1.0 / 64.0, 0.001, 4, cx.sp))
+    ch = B.Channelizer(offs, float(fs), 48e3, 48e3, 5e3)
+    assert (ch.tapCount, ch._interp, ch._decim) == (10241, 1, D)
+    stride = (n + lead) // D + 64
+    y = B.DevBuf(nch * stride * 4)
+    ch.seek(g0)
+
+    def step():
+        ch.process_device(x.ptr, y.ptr, n + lead, stride, blk, stream=cx.sp)
+
+    l0 = L.qdsp_launch_count()
+    step()
+    launches = L.qdsp_launch_count() - l0
+    ms, k, clocks = cx.timed(step, min_seconds=0.7, warmup=3)
+    # ---- oracle check on a fresh handle at this shard's stream position
+    ch0 = B.Channelizer(offs, float(fs), 48e3, 48e3, 5e3)
+    ch0.seek(g0)
+    m = ch0.process_device(x.ptr, y.ptr, n + lead, stride, blk, stream=cx.sp)
+    cx.torch.cuda.synchronize()
+    total = cx.world * n
+    worst, cnt = 0.0, 0
+    rng = np.random.default_rng(300 + cx.rank)
+    picks = sorted(set([0, nch - 1] + [int(c) for c in rng.integers(0, nch, size=4)]))
+    local = windows.pick_windows(n, blk, 2, 65536, [blk, blk * (n // blk)])
+    centres = [cx.rank * n + c for c in local]   # incl. the shard's first and last window: the seams between ranks
+    for c in picks:
+        a = np.zeros(total // D, dtype=np.float32)          # the whole stream's output axis; this rank fills its shard
+        got = dev_window(y.ptr, c * stride, c * stride + m, np.float32)
+        a[cx.rank * n // D:(cx.rank + 1) * n // D] = got[lead // D:]
+        w, k2 = windows.check_vfofm_windows(lambda lo, hi: dev_window(x.ptr, lo - g0, hi - g0), a, (cx.rank + 1) * n, blk, centres, 65536,
+                                            float(offs[c]), float(fs), 48e3, 48e3, 5e3, D, 10241)
+        worst = max(worst, w)
+        cnt += k2
+    worst = cx.allmax(worst)
+    alg = (n + lead) * 8 + nch * ((n + lead) // D) * 4
+    gbs = alg / ms / 1e6
+    res = {"workload": f"256-channel channelizer (VFO + FloatFMDemod per channel: 10241 taps, I=1, D=1280), FFT polyphase form: all 256 "
+                       f"channels on every GPU, a 61.44 MS/s stream of {total} cf32 time-sharded over {cx.world} GPU(s) "
+                       f"({n} samples + {lead} lead-in each), no collective",
+           "value": total / ms / 1e3, "unit": "Msamples/s (wideband input, all 256 channels produced)", "scaling": "weak",
+           "channel_msamples_s": nch * total / ms / 1e3, "ms_per_step": ms, "steps": k, "launches_per_step": int(launches), "clocks": clocks,
+           "roofline": {"bound": "hbm", "achieved": gbs, "unit": "GB/s", "peak": cx.hbm_peak, "frac": gbs / cx.hbm_peak,
+                        "alg_bytes_per_launch": alg, "note": "algorithmic bytes: the wideband input once + the 256 audio rows; the U/V "
+                        "planes between the two kernels (2 x 16 B per output row and channel) are extra traffic",
+                        "direct_form_equivalent_tflops_per_gpu": 38.0 * nch * (n + lead) / ms / 1e9},
+           "parity": {"oracle": "oracle/port.c reference chain (float64 rotator) per channel, windows incl. run() boundaries and both ends "
+                                "of this rank's shard (the seams between ranks)",
+                      "channels_checked_per_rank": len(picks), "outputs_compared_this_rank": cnt, "max_abs_err": worst, "tolerance_abs": 1e-4,
+                      "ok": bool(worst <= 1e-4)}}
+    x.free()
+    y.free()
+    return res
+
+
+def _cfg4_direct(cx: Ctx, fp32_peak):
     from oracle import loader, windows
     from qdsp_b200 import blocks as B, shard, synth
 
@@ -630,6 +708,7 @@ def run_cfg4(cx: Ctx, fp32_peak):
     x = B.DevBuf(n * 8)     # every rank holds the same wideband stream (generated in place: no broadcast on the timed path)
     lib.check(L.qdsp_synth_comb_cf32(x.ptr, 0, n, fs, nch_total, spacing, 5e3, 1.0 / 64.0, 0.001, 4, cx.sp))
     ch = B.Channelizer(offs, float(fs), 48e3, 48e3, 5e3)
+    ch.set_variant(2)
     assert (ch.tapCount, ch._interp, ch._decim) == (10241, 1, 1280)
     blk = 819200
     stride = n // 1280 + 64
@@ -641,6 +720,7 @@ def run_cfg4(cx: Ctx, fp32_peak):
     ms, k, clocks = cx.timed(step, min_seconds=1.0, warmup=1)
     # ---- oracle check on a fresh handle (first call of a stream), a few (channel, window) pairs incl. this rank's edge channels
     ch0 = B.Channelizer(offs, float(fs), 48e3, 48e3, 5e3)
+    ch0.set_variant(2)
     m = ch0.process_device(x.ptr, y.ptr, n, stride, blk, stream=cx.sp)
     cx.torch.cuda.synchronize()
     worst, cnt = 0.0, 0
@@ -658,7 +738,7 @@ def run_cfg4(cx: Ctx, fp32_peak):
         nch_total = nch
     tf = 38.0 * nch_total * n / ms / 1e9
     res = {"workload": f"{nch_total}-channel channelizer (VFO + FloatFMDemod per channel: 10241 taps, I=1, D=1280) off one 61.44 MS/s stream of "
-                       f"{n} cf32; {nch} channels on each of {cx.world} GPU(s), no collective",
+                       f"{n} cf32, DIRECT form; {nch} channels on each of {cx.world} GPU(s), no collective",
            "value": n / ms / 1e3, "unit": "Msamples/s (wideband input, all 256 channels produced)", "scaling": "strong",
            "channel_msamples_s": nch_total * n / ms / 1e3, "ms_per_step": ms, "steps": k, "clocks": clocks,
            "roofline": {"bound": "fp32", "achieved": tf, "unit": "TFLOP/s (all GPUs)", "per_gpu": tf / cx.world,
@@ -771,7 +851,7 @@ def ours(args):
     if "3" in want:
         configs["cfg3"] = run_cfg3(cx, fp32_peak)
     if "4" in want:
-        configs["cfg4"] = run_cfg4(cx, fp32_peak)
+        configs.update(run_cfg4(cx, fp32_peak))
     if "5" in want and cx.world == 1:
         configs.update(run_cfg5(cx))
     launches_total = int(L.qdsp_launch_count())

@@ -209,7 +209,14 @@ long long qdsp_channelizer_process(qdsp_channelizer* h, const void* in_dev, floa
                                    long long out_stride, long long count, const int* blocks, int nblocks,
                                    int block_size, qdsp_stream_t s);
 int qdsp_channelizer_reset(qdsp_channelizer* h);
+/* variant 0: the fastest path the geometry allows (a uniform comb of 256 channels fs / 256 apart with decimation 1280 --
+ * BASELINE config 4 -- takes the FFT polyphase kernels, k_chanfft.cu); 2: direct form (every channel its own VFO) always;
+ * 1: the generic kernels. */
 int qdsp_channelizer_set_variant(qdsp_channelizer* h, int variant);
+/* Time-sharding: the next call's first sample is sample `start` of the stream (the NCOs are closed-form in the position).
+ * A shard that starts mid-stream is fed max(history, decimation) extra samples ahead of its first wanted output and drops
+ * the outputs those produce (bench.py config 4 at N > 1). Extension: the reference's state is implicit in its run() order. */
+int qdsp_channelizer_seek(qdsp_channelizer* h, long long start);
 
 /* ---- recurrent blocks (chunked block-parallel scans) ----------------------------------------- */
 /* BFMDeemp::run, src/dsp/filter.h:129-158 (stereo_t in/out, state lastOutL/R) */

@@ -609,6 +609,10 @@ class Channelizer(_Block):
     def set_variant(self, v: int):
         _L().qdsp_channelizer_set_variant(self.h, v)
 
+    def seek(self, start: int):
+        """Time-sharding: the next call's first sample is sample `start` of the stream (include/qdsp_b200.h)."""
+        check(_L().qdsp_channelizer_seek(self.h, int(start)))
+
     def reset(self):
         check(_L().qdsp_channelizer_reset(self.h))
 

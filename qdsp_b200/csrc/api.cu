@@ -903,6 +903,10 @@ int qdsp_channelizer_set_variant(qdsp_channelizer* h, int variant) {
     h->variant = variant;
     return 0;
 }
+int qdsp_channelizer_seek(qdsp_channelizer* h, long long start) {
+    h->abs_pos = start;
+    return 0;
+}
 
 }  // extern "C"
 

@@ -20,31 +20,6 @@
 
 namespace qdsp {
 
-// packed f32x2 values as opaque 64-bit registers: built once per column pair, never re-materialised from their halves
-// (with float2 temporaries ptxas re-packs the (re, re) pairs in front of nearly every FFMA2: 880 MOVs per 512 FFMA2)
-typedef unsigned long long f32x2_t;
-__device__ __forceinline__ f32x2_t pk2(float a, float b) {
-    f32x2_t r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-    asm volatile("" : "+l"(r));
-    return r;
-}
-__device__ __forceinline__ float2 unpk2(f32x2_t v) {
-    float2 r;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
-    return r;
-}
-__device__ __forceinline__ f32x2_t ffma2x(f32x2_t a, f32x2_t b, f32x2_t c) {
-    f32x2_t d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ f32x2_t fmul2x(f32x2_t a, f32x2_t b) {
-    f32x2_t d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-
 template <int NPH, int Q, int DROW>
 struct FirRowArgs {
     const float2* hist;

@@ -122,6 +122,7 @@ SIGNATURES = {
     "qdsp_channelizer_process": (_ll, [_vp, _vp, _vp, _ll, _ll, _ip, _i, _i, _vp]),
     "qdsp_channelizer_reset": (_i, [_vp]),
     "qdsp_channelizer_set_variant": (_i, [_vp, _i]),
+    "qdsp_channelizer_seek": (_i, [_vp, _ll]),
     "qdsp_deemp_create": (_vp, [_f, _f]),
     "qdsp_deemp_destroy": (None, [_vp]),
     "qdsp_deemp_process": (_ll, [_vp, _vp, _vp, _ll, _vp]),
