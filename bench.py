@@ -634,8 +634,13 @@ def _cfg4_fft(cx: Ctx):
     L, lib = cx.L, cx.lib
     n, nch = cx.args.n4, 256
     fs, spacing, D, blk = 61_440_000, 240_000, 1280, 819200
+    # shard r = [s_r, s_{r+1}) of the N * 2^26-sample stream, s_r on the decimation grid (2^26 is not a multiple of 1280)
+    total = cx.world * n
+    cut = lambda r: total if r >= cx.world else (r * n // D) * D
+    lo, hi = cut(cx.rank), cut(cx.rank + 1)
     lead = 16 * D if cx.rank > 0 else 0          # >= history (10 240) + one row for the demodulator's previous angle
-    g0 = cx.rank * n - lead                      # stream position of this rank's first local sample
+    g0 = lo - lead                               # stream position of this rank's first local sample
+    n = hi - lo
     offs = synth.cfg4_offsets(nch, spacing)
     x = B.DevBuf((n + lead) * 8)
     lib.check(L.qdsp_synth_comb_cf32(x.ptr, g0, n + lead, fs, nch, spacing, 5e3, 1.0 / 64.0, 0.001, 4, cx.sp))
@@ -657,17 +662,16 @@ def _cfg4_fft(cx: Ctx):
     ch0.seek(g0)
     m = ch0.process_device(x.ptr, y.ptr, n + lead, stride, blk, stream=cx.sp)
     cx.torch.cuda.synchronize()
-    total = cx.world * n
     worst, cnt = 0.0, 0
     rng = np.random.default_rng(300 + cx.rank)
     picks = sorted(set([0, nch - 1] + [int(c) for c in rng.integers(0, nch, size=4)]))
     local = windows.pick_windows(n, blk, 2, 65536, [blk, blk * (n // blk)])
-    centres = [cx.rank * n + c for c in local]   # incl. the shard's first and last window: the seams between ranks
+    centres = [lo + c for c in local]            # incl. the shard's first and last window: the seams between ranks
     for c in picks:
         a = np.zeros(total // D, dtype=np.float32)          # the whole stream's output axis; this rank fills its shard
         got = dev_window(y.ptr, c * stride, c * stride + m, np.float32)
-        a[cx.rank * n // D:(cx.rank + 1) * n // D] = got[lead // D:]
-        w, k2 = windows.check_vfofm_windows(lambda lo, hi: dev_window(x.ptr, lo - g0, hi - g0), a, (cx.rank + 1) * n, blk, centres, 65536,
+        a[lo // D:lo // D + n // D] = got[lead // D:lead // D + n // D]
+        w, k2 = windows.check_vfofm_windows(lambda l, h: dev_window(x.ptr, l - g0, h - g0), a, hi, blk, centres, 65536,
                                             float(offs[c]), float(fs), 48e3, 48e3, 5e3, D, 10241)
         worst = max(worst, w)
         cnt += k2
@@ -676,7 +680,7 @@ def _cfg4_fft(cx: Ctx):
     gbs = alg / ms / 1e6
     res = {"workload": f"256-channel channelizer (VFO + FloatFMDemod per channel: 10241 taps, I=1, D=1280), FFT polyphase form: all 256 "
                        f"channels on every GPU, a 61.44 MS/s stream of {total} cf32 time-sharded over {cx.world} GPU(s) "
-                       f"({n} samples + {lead} lead-in each), no collective",
+                       f"({n} samples + {lead} lead-in on this rank), no collective",
            "value": total / ms / 1e3, "unit": "Msamples/s (wideband input, all 256 channels produced)", "scaling": "weak",
            "channel_msamples_s": nch * total / ms / 1e3, "ms_per_step": ms, "steps": k, "launches_per_step": int(launches), "clocks": clocks,
            "roofline": {"bound": "hbm", "achieved": gbs, "unit": "GB/s", "peak": cx.hbm_peak, "frac": gbs / cx.hbm_peak,
