@@ -744,17 +744,19 @@ def test_fft_polyphase_channelizer_matches_direct_form_and_oracle():
     for c in (0, 1, 100, 128, 255):
         a64, _ = P.vfo_fm(float(offs[c]), 61.44e6, 48e3, 48e3, 5e3, x, blk, nco_f64=True)
         assert np.abs(y[c][16:] - a64[16:]).max() <= AUDIO_TOL, (c, np.abs(y[c][16:] - a64[16:]).max())
-    # the same comb moved half a bin up: channel 0 on the bin grid (no twist, no tap sign alternation in k_chanfft.cu)
-    sh = np.exp(2j * np.pi * synth._frac(np.arange(n, dtype=np.int64), 120_000, 61_440_000))
-    x2 = (x.astype(np.complex128) * sh).astype(np.complex64)
-    offs2 = (offs + np.float32(120_000)).astype(np.float32)
-    g = B.Channelizer(offs2, 61.44e6, 48e3, 48e3, 5e3)
-    gd = B.Channelizer(offs2, 61.44e6, 48e3, 48e3, 5e3)
-    gd.set_variant(2)
-    yg, ygd = g.process(x2, blk), gd.process(x2, blk)
-    assert np.abs(yg[:, 16:] - ygd[:, 16:]).max() <= AUDIO_TOL, np.abs(yg[:, 16:] - ygd[:, 16:]).max()
-    a64, _ = P.vfo_fm(float(offs2[37]), 61.44e6, 48e3, 48e3, 5e3, x2, blk, nco_f64=True)
-    assert np.abs(yg[37][16:] - a64[16:]).max() <= AUDIO_TOL
+    # the same comb moved half a bin up (channel 0 on the bin grid: no twist, no tap sign alternation in k_chanfft.cu) and by
+    # 50 kHz (on neither grid: the column filter pre-rotates the stream by channel 0's NCO)
+    for shift in (120_000, 50_000):
+        sh = np.exp(2j * np.pi * synth._frac(np.arange(n, dtype=np.int64), shift, 61_440_000))
+        x2 = (x.astype(np.complex128) * sh).astype(np.complex64)
+        offs2 = (offs + np.float32(shift)).astype(np.float32)
+        g = B.Channelizer(offs2, 61.44e6, 48e3, 48e3, 5e3)
+        gd = B.Channelizer(offs2, 61.44e6, 48e3, 48e3, 5e3)
+        gd.set_variant(2)
+        yg, ygd = g.process(x2, blk), gd.process(x2, blk)
+        assert np.abs(yg[:, 16:] - ygd[:, 16:]).max() <= AUDIO_TOL, (shift, np.abs(yg[:, 16:] - ygd[:, 16:]).max())
+        a64, _ = P.vfo_fm(float(offs2[37]), 61.44e6, 48e3, 48e3, 5e3, x2, blk, nco_f64=True)
+        assert np.abs(yg[37][16:] - a64[16:]).max() <= AUDIO_TOL, shift
     # streamed: the third call starts off the decimation grid (every run() block restarts the grid, resampling.h:99-132), so
     # its outputs sit elsewhere than the one-call run's; the direct form over the same cuts is the comparison there
     s = B.Channelizer(offs, 61.44e6, 48e3, 48e3, 5e3)
