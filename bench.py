@@ -629,18 +629,18 @@ def run_cfg4(cx: Ctx, fp32_peak):
 
 def _cfg4_fft(cx: Ctx):
     from oracle import windows
-    from qdsp_b200 import blocks as B, synth
+    from qdsp_b200 import blocks as B, shard, synth
 
     L, lib = cx.L, cx.lib
     n, nch = cx.args.n4, 256
     fs, spacing, D, blk = 61_440_000, 240_000, 1280, 819200
-    # shard r = [s_r, s_{r+1}) of the N * 2^26-sample stream, s_r on the decimation grid (2^26 is not a multiple of 1280)
+    # shard r = [s_r, s_{r+1}) of the N * 2^26-sample stream, s_r on the decimation grid (2^26 is not a multiple of 1280);
+    # lead-in: history (10 240 samples) + one row for the demodulator's previous angle + margin = 16 rows
     total = cx.world * n
-    cut = lambda r: total if r >= cx.world else (r * n // D) * D
-    lo, hi = cut(cx.rank), cut(cx.rank + 1)
-    lead = 16 * D if cx.rank > 0 else 0          # >= history (10 240) + one row for the demodulator's previous angle
+    me = shard.lead_in_shards(n, cx.world, D, 10241, extra_rows=6)[cx.rank]
+    lo, hi, lead = me.start, me.start + me.count, me.lead
     g0 = lo - lead                               # stream position of this rank's first local sample
-    n = hi - lo
+    n = me.count
     offs = synth.cfg4_offsets(nch, spacing)
     x = B.DevBuf((n + lead) * 8)
     lib.check(L.qdsp_synth_comb_cf32(x.ptr, g0, n + lead, fs, nch, spacing, 5e3, 1.0 / 64.0, 0.001, 4, cx.sp))

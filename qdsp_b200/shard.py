@@ -53,6 +53,35 @@ def time_shards(total: int, world: int, block: int, history: int) -> list[TimeSh
     return shards
 
 
+@dataclass(frozen=True)
+class LeadShard:
+    rank: int
+    start: int        # first sample whose outputs this rank keeps (absolute stream index, on the decimation grid)
+    count: int        # samples in the shard
+    lead: int         # samples ahead of `start` the rank also consumes; the lead // decim outputs they produce are dropped
+    first_out: int    # global index of the first output the rank keeps
+
+
+def lead_in_shards(per_rank: int, world: int, decim: int, taps: int, extra_rows: int = 0) -> list[LeadShard]:
+    """Time shards of a decimating chain that need NO exchange: a stream of world * per_rank samples is cut on the
+    decimation grid (run() blocks that are multiples of `decim` keep every output on that grid, resampling.h:121), and
+    every rank but the first is handed `lead` more samples ahead of its shard: enough rows for the filter history
+    (taps samples) plus one for the FM demodulator's previous phase (demodulator.h:88-92). The rank seeks its handle to
+    start - lead (the NCO is closed-form in the stream position), processes lead + count samples and drops the first
+    lead // decim outputs. Used by the FFT-form channelizer at N > 1 (bench.py cfg4)."""
+    if per_rank < 0 or world < 1 or decim < 1 or taps < 1:
+        raise ValueError("bad arguments")
+    total = world * per_rank
+    rows = -(-taps // decim) + 1 + extra_rows    # the resampler's history is tapsPerPhase = taps samples (resampling.h:129)
+    cut = lambda r: total if r >= world else (r * per_rank // decim) * decim
+    out = []
+    for r in range(world):
+        lo, hi = cut(r), cut(r + 1)
+        lead = min(rows * decim, lo) if r > 0 else 0
+        out.append(LeadShard(r, lo, hi - lo, lead, lo // decim))
+    return out
+
+
 def halo_sources(shards: list[TimeShard], rank: int) -> list[tuple[int, int, int]]:
     """Which ranks own rank's halo: list of (src_rank, src_offset_in_its_shard, n) in stream order. Normally one
     entry (the previous rank's tail); more only when shards are shorter than the history."""

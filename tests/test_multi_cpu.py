@@ -84,3 +84,65 @@ def test_time_sharded_fir_equals_unsharded(world, total, block, T):
     ref = loader.port().fir_cf32(taps, synth.uniform_cf32(3, 0, total))
     assert y.shape == ref.shape
     assert np.array_equal(y.view(np.uint32), ref.view(np.uint32)), "time-sharded FIR must be bit-identical to the unsharded run"
+
+
+def test_lead_in_shards_cover_stream_on_decimation_grid():
+    for per, world, D, T in [(1 << 26, 8, 1280, 10241), (100_030, 3, 50, 401), (5000, 2, 50, 401), (7, 4, 50, 401)]:
+        sh = shard.lead_in_shards(per, world, D, T)
+        assert sum(s.count for s in sh) == per * world and sh[0].start == 0 and sh[0].lead == 0
+        for a, b in zip(sh[:-1], sh[1:]):
+            assert a.start + a.count == b.start and b.start % D == 0 and b.first_out == b.start // D
+            assert b.lead % D == 0 and (b.lead >= T + D or b.lead == b.start)
+
+
+def _lead_worker(rank, world, port, per, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import loader
+
+        P = loader.port()
+        D, T, blk = 50, 401, 4000
+        me = shard.lead_in_shards(per, world, D, T)[rank]
+        g0 = me.start - me.lead
+        x = synth.fm_cf32(g0, me.lead + me.count, 2_400_000, 250_000, 1000, 5e3, 0.5) + np.float32(0.01) * synth.uniform_cf32(1, g0, me.lead + me.count)
+        # what the GPU rank does: seek to g0, process lead + count samples in run() blocks, drop the lead-in outputs
+        a, _, _ = P.vfo_fm_window(250e3, 2.4e6, 48e3, 48e3, 5e3, x.astype(np.complex64), blk, g0)
+        keep = torch.from_numpy(a[me.lead // D:].copy())
+        sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(sizes, torch.tensor([keep.numel()], dtype=torch.int64))
+        bufs = [torch.zeros(int(s), dtype=torch.float32) for s in sizes]
+        if rank == 0:
+            bufs[0] = keep
+            for r in range(1, world):
+                dist.recv(bufs[r], src=r)
+            q.put(torch.cat(bufs).numpy())
+        else:
+            dist.send(keep, dst=0)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_lead_in_time_shards_equal_unsharded_chain():
+    """World-size-2 gloo run of the no-exchange time sharding the FFT-form channelizer uses at N > 1 (bench.py cfg4): every
+    rank runs the oracle chain over lead-in + shard at its stream position and drops the lead-in outputs; the gathered
+    audio equals the unsharded run."""
+    from oracle import loader
+
+    world, per = 2, 60_030
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_lead_worker, args=(r, world, port, per, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    total = world * per
+    x = synth.fm_cf32(0, total, 2_400_000, 250_000, 1000, 5e3, 0.5) + np.float32(0.01) * synth.uniform_cf32(1, 0, total)
+    ref, _, _ = loader.port().vfo_fm_window(250e3, 2.4e6, 48e3, 48e3, 5e3, x.astype(np.complex64), 4000, 0)
+    assert got.shape == ref.shape
+    assert np.abs(got[16:] - ref[16:]).max() <= 1e-6, np.abs(got[16:] - ref[16:]).max()
