@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(kCfM, 2) chanfft_fft_kernel(const ChanFftBArgs
     const long long mm = m < 0 ? 0 : (m >= a.total_out ? a.total_out - 1 : m);
     {
         float sn, cs;
-        sincospif(-(float)t / 128.0f, &sn, &cs);                   // e^{-j 2 pi t / 256}
+        sincospif(-(float)(f * c) / 128.0f, &sn, &cs);             // tw[k1][n2] = W256^{n2 k1}: lanes read consecutive entries
         tw[t] = make_float2(cs, sn);
     }
     float2 u[16], v[16];
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(kCfM, 2) chanfft_fft_kernel(const ChanFftBArgs
     float2* sv = sV + f * (16 * kCfLd);
 #pragma unroll
     for (int k1 = 0; k1 < 16; k1++) {
-        const float2 w = tw[(c * k1) & (kCfM - 1)];
+        const float2 w = tw[k1 * 16 + c];
         su[k1 * kCfLd + c] = cmul(u[bitrev4(k1)], w);
         sv[k1 * kCfLd + c] = cmul(v[bitrev4(k1)], w);
     }

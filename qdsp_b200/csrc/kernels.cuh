@@ -99,6 +99,10 @@ int launch_firrow(const float* taps_host, int T, int D, const float2* hist, floa
 // ---- k_recurrent.cu -----------------------------------------------------------------------------
 int launch_deemp(const float2* in, float2* out, long long count, float alpha, float* state, void* scratch,
                  size_t scratch_bytes, cudaStream_t s);
+int agc_fused_chunk_blocks(const Partition& part, const float* in, const float* out);
+size_t agc_fused_scratch_bytes(int cb);
+int launch_agc_fused(const float* in, float* out, const Partition& part, float corrected_fall_rate, float* level_state, void* scratch,
+                     int cb, cudaStream_t s);
 int launch_agc(const float* in, float* out, const Partition& part, float corrected_fall_rate, float* level_state,
                float* blockmax_scratch, float* level_scratch, cudaStream_t s);
 int launch_cagc(const float2* in, float2* out, long long count, float set_point, float max_gain, float rate,

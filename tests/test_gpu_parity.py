@@ -768,3 +768,25 @@ def test_fft_polyphase_channelizer_matches_direct_form_and_oracle():
     assert parts.shape == partsd.shape == y.shape
     assert np.abs(parts[:, 16:131] - y[:, 16:131]).max() <= 2e-5, np.abs(parts[:, 16:131] - y[:, 16:131]).max()
     assert np.abs(parts[:, 16:] - partsd[:, 16:]).max() <= AUDIO_TOL, np.abs(parts[:, 16:] - partsd[:, 16:]).max()
+
+
+def test_agc_fused_persistent_kernel_long_batch():
+    # >= 64 MiB in run() blocks of >= 1 MiB takes the single-launch kernel (chunks of blocks, grid barrier, the second read
+    # of a chunk served by L2); ragged last block, level state carried into a second call; against the oracle as a whole
+    from qdsp_b200 import blocks as B, synth
+
+    P = loader.port()
+    n = (1 << 25) + 12345
+    x = synth.uniform_f32(67, 0, n)
+    x *= (1.0 + 0.5 * np.sin(np.arange(n, dtype=np.float32) * np.float32(2e-6))).astype(np.float32)
+    agc = B.AGC(20.0, 48e3)
+    y1 = agc.process(x[: n // 2], 1_000_000)          # 16.8 M floats: fused path
+    y2 = agc.process(x[n // 2:], 1_000_000)
+    yo1 = P.agc(20.0, 48e3, x[: n // 2], 1_000_000)
+    assert np.max(np.abs(y1 - yo1)) <= 1e-5 * max(1.0, float(np.max(np.abs(yo1))))
+    # second call continues from the first call's level: oracle over the concatenation with the same run() cuts
+    cuts = [1_000_000] * ((n // 2) // 1_000_000) + [(n // 2) % 1_000_000]
+    rest = n - n // 2
+    cuts += [1_000_000] * (rest // 1_000_000) + [rest % 1_000_000]
+    yo = P.agc(20.0, 48e3, x, [c for c in cuts if c > 0])
+    assert np.max(np.abs(np.concatenate([y1, y2]) - yo)) <= 1e-5 * max(1.0, float(np.max(np.abs(yo))))
