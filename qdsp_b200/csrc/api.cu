@@ -1016,8 +1016,8 @@ long long qdsp_agc_process(qdsp_agc* h, const float* in_dev, float* out_dev, lon
     // long batches of large run() blocks: one persistent launch, the second read of every chunk served by L2
     if (const int cb = agc_fused_chunk_blocks(h->part, in_dev, out_dev)) {
         if (h->scratch.reserve(agc_fused_scratch_bytes(cb)) != 0) return -1;
-        if (launch_agc_fused(in_dev, out_dev, h->part, h->corrected, h->st.p, h->scratch.p, cb, s) != 0) return -1;
-        return count;
+        if (launch_agc_fused(in_dev, out_dev, h->part, h->corrected, h->st.p, h->scratch.p, cb, s) == 0) return count;
+        cudaGetLastError();     // a refused cooperative launch has run nothing: take the three-kernel path below
     }
     // scratch: [nb][32] partial maxima of the block-max pass, then [nb] reciprocal levels
     if (h->scratch.reserve(sizeof(float) * 33 * (size_t)nb + 64) != 0) return -1;

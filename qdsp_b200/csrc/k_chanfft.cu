@@ -515,7 +515,10 @@ int launch_chanfft(ChanFftPlan* plan, const float2* hist, int H, const float2* i
     a.twist = (!plan->rotate && (plan->twob & 1)) ? 1 : 0;
     const size_t smem = (size_t)kCfStages * kCfDR * kCfM * 8 + (size_t)2 * kCfStages * 8 + 16;
     const size_t smem_b = (size_t)2 * kCfRB * 16 * kCfLd * sizeof(float2) + kCfM * sizeof(float2) + (size_t)kCfRB * (kCfM + 1) * sizeof(float);
-    static bool attr = false;
+    static bool attr_dev[64] = {};      // opt-in shared memory is a per-device function attribute
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool& attr = attr_dev[dev & 63];
     if (!attr) {
         QDSP_CUDA_OK(cudaFuncSetAttribute(chanfft_poly_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         QDSP_CUDA_OK(cudaFuncSetAttribute(chanfft_poly_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
