@@ -27,7 +27,7 @@ constexpr int kFirNout = (kFirWarps / 2) * 64 * kFirR;   // 2304 outputs per til
 
 struct FirPlan {
     int T = 0;
-    int U = 0;                  // tap pairs per parity table, multiple of kFirR
+    int U = 0;                  // tap pairs per parity table
     float2* taps_dev = nullptr; // [2][U]: even table (h[2u], h[2u+1]); odd table (h[2u-1], h[2u])
 };
 
@@ -37,8 +37,9 @@ FirPlan* fir_plan_create(const float* taps, int T) {
     if (!p) return nullptr;
     p->T = T;
     int U = (T + 2) / 2;                        // enough pairs for the odd table's extra leading zero
-    U = ((U + kFirR - 1) / kFirR) * kFirR;
-    p->U = U;
+    const int Upad = ((U + kFirR - 1) / kFirR) * kFirR;
+    if ((Upad - U) * 33 <= U) U = Upad;         // long filters: round up to whole groups of R (< 3 % more work, leaner kernel);
+    p->U = U;                                   // short ones end inside the last group (127 taps: 64 pairs, not 72)
     // shared memory: quads for NOUT/2 + U pairs (+ slack) and both tap tables
     const size_t smem = ((size_t)kFirNout / 2 + U + 8) * 16 + (size_t)2 * U * 8;
     if (smem > 110 * 1024) {                    // keep two CTAs per SM; longer filters use the generic kernel
@@ -82,7 +83,7 @@ __device__ __forceinline__ void store_tile(const float2* so, float2* __restrict_
     }
 }
 
-template <int NW>
+template <int NW, bool TAIL>
 __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 4)
 fir_dense_kernel(VStream<float2> xs, long long count, const float2* __restrict__ taps, int T, int U,
                  float2* __restrict__ out) {
@@ -184,8 +185,9 @@ fir_dense_kernel(VStream<float2> xs, long long count, const float2* __restrict__
         W[i] = win[i];
     }
     // output i accumulates H_u (.) S_{j0 + i + u}; window register W[(u + i) % R] holds S_{j0 + i + u}
+    const int Ufull = (U / R) * R;
 #pragma unroll 1
-    for (int u0 = 0; u0 < U; u0 += R) {
+    for (int u0 = 0; u0 < Ufull; u0 += R) {
 #pragma unroll
         for (int k = 0; k < R; k++) {
             const float2 hh = tt[u0 + k];
@@ -196,6 +198,20 @@ fir_dense_kernel(VStream<float2> xs, long long count, const float2* __restrict__
                 accIm[i] = __ffma2_rn(make_float2(s.z, s.w), hh, accIm[i]);
             }
             W[k] = win[u0 + k + R];               // S_{j0 + (u0+k+1) + (R-1)} replaces S_{j0 + u0 + k}
+        }
+    }
+    // the last, partial group of R (TAIL: U is not a multiple of R -- 127 taps are 64 pairs, not 72)
+#pragma unroll
+    for (int k = 0; k < R - 1; k++) {
+        if (TAIL && Ufull + k < U) {
+            const float2 hh = tt[Ufull + k];
+#pragma unroll
+            for (int i = 0; i < R; i++) {
+                const float4 s = W[(k + i) % R];
+                accRe[i] = __ffma2_rn(make_float2(s.x, s.y), hh, accRe[i]);
+                accIm[i] = __ffma2_rn(make_float2(s.z, s.w), hh, accIm[i]);
+            }
+            W[k] = win[Ufull + k + R];
         }
     }
     // ---- store: outputs n = n_t + 2*(j0 + i) + parity. A thread's outputs are 16 bytes apart and the lanes 144:
@@ -434,11 +450,19 @@ int launch_fir_dense(FirPlan* plan, const float2* hist, int H, const float2* in,
     const size_t smem = ((size_t)nout / 2 + plan->U + 8) * 16 + (size_t)2 * plan->U * 8;
     const long long tiles = (count + nout - 1) / nout;
     if (NW == 4) {
-        QDSP_CUDA_OK(cudaFuncSetAttribute(fir_dense_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-        fir_dense_kernel<4><<<(unsigned)tiles, 128, smem, s>>>(xs, count, plan->taps_dev, plan->T, plan->U, out);
+        QDSP_CUDA_OK(cudaFuncSetAttribute(fir_dense_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        QDSP_CUDA_OK(cudaFuncSetAttribute(fir_dense_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        if (plan->U % kFirR)
+            fir_dense_kernel<4, true><<<(unsigned)tiles, 128, smem, s>>>(xs, count, plan->taps_dev, plan->T, plan->U, out);
+        else
+            fir_dense_kernel<4, false><<<(unsigned)tiles, 128, smem, s>>>(xs, count, plan->taps_dev, plan->T, plan->U, out);
     } else {
-        QDSP_CUDA_OK(cudaFuncSetAttribute(fir_dense_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-        fir_dense_kernel<8><<<(unsigned)tiles, 256, smem, s>>>(xs, count, plan->taps_dev, plan->T, plan->U, out);
+        QDSP_CUDA_OK(cudaFuncSetAttribute(fir_dense_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        QDSP_CUDA_OK(cudaFuncSetAttribute(fir_dense_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        if (plan->U % kFirR)
+            fir_dense_kernel<8, true><<<(unsigned)tiles, 256, smem, s>>>(xs, count, plan->taps_dev, plan->T, plan->U, out);
+        else
+            fir_dense_kernel<8, false><<<(unsigned)tiles, 256, smem, s>>>(xs, count, plan->taps_dev, plan->T, plan->U, out);
     }
     QDSP_LAUNCH_OK();
     return 0;
