@@ -790,3 +790,60 @@ def test_agc_fused_persistent_kernel_long_batch():
     cuts += [1_000_000] * (rest // 1_000_000) + [rest % 1_000_000]
     yo = P.agc(20.0, 48e3, x, [c for c in cuts if c > 0])
     assert np.max(np.abs(np.concatenate([y1, y2]) - yo)) <= 1e-5 * max(1.0, float(np.max(np.abs(yo))))
+
+
+def test_ffagc_streaming_kernel_long_ragged_bit_exact():
+    # the run-of-segments FeedForwardAGC kernel: many CTAs x many segments, odd pending counts between calls (the
+    # segment grid is then never 16-byte aligned with the input), zero and tiny samples (library division instead of the
+    # shared-reciprocal fast path), a call shorter than the window; bit-for-bit against the oracle over the whole stream
+    from qdsp_b200 import blocks as B, synth
+
+    P = loader.port()
+    n = 3_300_123
+    x = synth.qpsk_cf32(31, 0, n, am_depth=0.7, am_period=5000)
+    x[70_000:73_500] = 0                       # a window of exact zeros: level floor 1e-4, 0 / level
+    x[150_001] = np.complex64(1e-30 + 3e-25j)  # below the fast-division range
+    x[150_777] = np.complex64(complex(-0.0, 0.0))
+    x[1_000_000:1_000_050] *= np.float32(3e4)  # a burst that owns 1024 windows
+    yo = P.ff_agc(x)
+    g = B.FeedForwardAGC()
+    cuts = [0, 500, 1100, 1101, 250_000, 250_007, 2_000_000, n]
+    y = np.concatenate([g.process(x[a:b]) for a, b in zip(cuts[:-1], cuts[1:])])
+    assert y.shape == yo.shape
+    assert np.array_equal(y.view(np.uint32), yo.view(np.uint32))
+
+
+def test_ffagc_streaming_kernel_float_bit_exact():
+    # float streams (amplitude = |x|): against a numpy sliding maximum with IEEE float32 division
+    from qdsp_b200 import blocks as B, synth
+
+    n = 200_003
+    x = synth.uniform_f32(5, 0, n)
+    x *= (1.0 + 0.9 * np.sin(np.arange(n, dtype=np.float32) * np.float32(1e-3))).astype(np.float32)
+    x[30_000:32_000] = 0
+    amp = np.abs(x)
+    w = np.lib.stride_tricks.sliding_window_view(amp, 1024).max(axis=1)
+    level = np.maximum(w, np.float32(1e-4)).astype(np.float32)
+    yo = (x[: len(level)] / level).astype(np.float32)
+    g = B.FeedForwardAGC(np.float32)
+    cuts = [0, 1023, 1024, 5001, 100_000, n]
+    y = np.concatenate([g.process(x[a:b]) for a, b in zip(cuts[:-1], cuts[1:])])
+    assert y.shape == yo.shape
+    assert np.array_equal(y.view(np.uint32), yo.view(np.uint32))
+
+
+def test_complex_agc_lookback_zero_runs_and_both_tile_sizes():
+    # interior tiles take the check-free path with the branch-free square root; runs of exact zeros (amplitude 0) and the
+    # ragged last tile take the guarded one
+    from qdsp_b200 import blocks as B, synth
+
+    P = loader.port()
+    n = 1_000_003
+    x = synth.qpsk_cf32(41, 0, n, am_depth=0.5, am_period=7000)
+    x[123_000:131_500] = 0
+    x[500_000] = 0
+    yo = P.complex_agc(1.0, 65535.0, 1e-3, x)
+    c = B.ComplexAGC(1.0, 65535.0, 1e-3)
+    y = c.process(x)
+    assert np.all(np.isfinite(y.view(np.float32)))
+    assert rel_l2(y, yo) <= 1e-4, rel_l2(y, yo)
