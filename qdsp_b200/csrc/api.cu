@@ -1109,6 +1109,19 @@ qdsp_costas* qdsp_costas_create(int order, float loopBandwidth) {
     const float den = (float)(1.0 + 2.0 * damp * loopBandwidth + loopBandwidth * loopBandwidth);
     h->alpha = (4 * damp * loopBandwidth) / den;
     h->beta = (4 * loopBandwidth * loopBandwidth) / den;
+    // default warm-up: the chunk walks start from (carried frequency, phase 0) and must have merged with the true
+    // trajectory when their chunk begins. Measured against the sequential loop at loopBandwidth 0.004 (700 001 samples):
+    // ORDER 4 needs 2048 samples (4e-6), the BPSK detector (error = re * im) 4096, the 8-PSK detector (the smaller branch
+    // weighted by sqrt(2) - 1) 8192; the loop's time constant scales with 1 / loopBandwidth. `qdsp_costas_last_residual`
+    // reports the largest boundary mismatch of every call: it is the validity check for other signals / bandwidths.
+    {
+        const double scale = order == 2 ? 2.0 : (order == 8 ? 4.0 : 1.0);
+        double w = 8.192 / (loopBandwidth > 1e-6f ? (double)loopBandwidth : 1e-6) * scale;
+        if (w < 256.0) w = 256.0;
+        if (w > 65536.0) w = 65536.0;
+        h->warmup = ((int)w + 15) / 16 * 16;
+        h->chunk = h->warmup > 2048 ? h->warmup : 2048;
+    }
     if (const char* e = getenv("QDSP_COSTAS_CHUNK")) {      // A/B switches
         h->chunk = atoi(e) >= 16 ? atoi(e) / 16 * 16 : h->chunk;
         h->chunk_user = true;
@@ -1131,7 +1144,7 @@ long long qdsp_costas_process(qdsp_costas* h, const void* in_dev, void* out_dev,
     }
     // the work is (1 + warmup / chunk) x the sequential loop's: with >= 32768 chunks of 4096 samples the machine is still full
     // (B200, 2^28 QPSK samples, GS/s: chunk 2048: 95, 3072: 95, 4096: 110, 8192: 103; warm-up 2048 throughout)
-    const int chunk = (!h->chunk_user && count >= (1ll << 27)) ? 4096 : h->chunk;
+    const int chunk = (!h->chunk_user && count >= (1ll << 27) && h->chunk < 4096) ? 4096 : h->chunk;
     if (h->scratch.reserve(costas_scratch_bytes(count, chunk)) != 0) return -1;
     if (launch_costas((const float2*)in_dev, (float2*)out_dev, count, h->order, h->alpha, h->beta, h->st.p, chunk,
                       h->warmup, h->scratch.p, h->scratch.cap, h->st.p + 4, as_stream(s)) != 0)

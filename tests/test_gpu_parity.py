@@ -847,3 +847,21 @@ def test_complex_agc_lookback_zero_runs_and_both_tile_sizes():
     y = c.process(x)
     assert np.all(np.isfinite(y.view(np.float32)))
     assert rel_l2(y, yo) <= 1e-4, rel_l2(y, yo)
+
+
+@pytest.mark.parametrize("order,gen", [(4, "qpsk"), (2, "bpsk"), (8, "qpsk")])
+def test_costas_chunked_default_warmup_ragged_streaming(order, gen):
+    # the library's default (order- and bandwidth-dependent) warm-up on every detector: odd sample counts (a step that ends
+    # inside the last chunk), a CTA whose chunks are only partly inside the stream, the loop state carried across three
+    # calls, the coalesced three-kernel stitch; the boundary residual must certify the result
+    from qdsp_b200 import blocks as B, synth
+
+    n = 700_001
+    x = (synth.qpsk_cf32 if gen == "qpsk" else synth.bpsk_cf32)(35, 0, n)
+    yo, st = loader.port().costas(order, 0.004, x)
+    pl = B.CostasLoop(order, 0.004)
+    cuts = [0, 300_003, 300_003 + 2048 * 37 + 5, n]
+    y = np.concatenate([pl.process(x[a:b]) for a, b in zip(cuts[:-1], cuts[1:])])
+    assert pl.last_residual() < 1e-4
+    assert y.shape == yo.shape
+    assert np.abs(y - yo).max() <= 1e-4, np.abs(y - yo).max()
