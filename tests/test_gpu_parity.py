@@ -865,3 +865,31 @@ def test_costas_chunked_default_warmup_ragged_streaming(order, gen):
     assert pl.last_residual() < 1e-4
     assert y.shape == yo.shape
     assert np.abs(y - yo).max() <= 1e-4, np.abs(y - yo).max()
+
+
+def test_costas_warp_staged_kernel_opt_in():
+    # QDSP_COSTAS_WARP=1 (read once per process, hence the subprocess): the warp-private cp.async walk against the
+    # sequential oracle on a ragged three-call stream, all three detectors
+    import os
+    import subprocess
+    import sys
+
+    code = r"""
+import numpy as np
+from oracle import loader
+from qdsp_b200 import blocks as B, synth
+n = 700_001
+for order, gen in [(4, synth.qpsk_cf32), (2, synth.bpsk_cf32), (8, synth.qpsk_cf32)]:
+    x = gen(35, 0, n)
+    yo, _ = loader.port().costas(order, 0.004, x)
+    pl = B.CostasLoop(order, 0.004)
+    cuts = [0, 300_003, 300_003 + 2048 * 37 + 5, n]
+    y = np.concatenate([pl.process(x[a:b]) for a, b in zip(cuts[:-1], cuts[1:])])
+    assert pl.last_residual() < 1e-4, pl.last_residual()
+    assert np.abs(y - yo).max() <= 1e-4, (order, np.abs(y - yo).max())
+print("ok")
+"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, QDSP_COSTAS_WARP="1", PYTHONPATH=root)
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
