@@ -191,6 +191,143 @@ __global__ void __launch_bounds__(32) fir_rowphase_kernel(const __grid_constant_
     }
 }
 
+// ---- complex-pair variant ----------------------------------------------------------------------------------------
+// Same tiling, staging and output gather; the packed operand is the SAMPLE as it lies in shared memory, (re, im), and the
+// tap enters both halves: acc(re, im) += x(re, im) * (g, g). No (re, re) / (im, im) re-pairing (the FMUL2-by-one packs
+// above: 3.9 per sample), no horizontal add before the gather (2.9 FADD per sample): the FMA pipe carries the algorithmic
+// FFMA2 and the gather's FADD2 only.
+template <int D, int DROW, int Q, int T, int PAD, int NSTG>
+__global__ void __launch_bounds__(32) fir_rowcplx_kernel(const __grid_constant__ FirRowArgs<DROW / D, Q, DROW> fa) {
+    constexpr int NPH = DROW / D;
+    constexpr int PITCH = DROW * 8;
+    constexpr uint32_t STAGE_BYTES = 32u * PITCH;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x;
+    const int rows_per_tile = 32 * fa.nstep - (Q - 1);
+    const long long row_t0 = (long long)blockIdx.x * rows_per_tile;
+    const long long nrows_total = (fa.n_out + NPH - 1) / NPH;
+    if (fa.hist_next != nullptr && blockIdx.x == 0) {
+        for (int j = lane; j < fa.H; j += 32) {
+            const long long v = fa.count - fa.H + j;
+            fa.hist_next[j] = v >= 0 ? fa.in[v] : fa.hist[fa.H + v];
+        }
+    }
+    if (row_t0 >= nrows_total) return;
+    const long long left = nrows_total - row_t0;
+    const int nrows_emit = left < rows_per_tile ? (int)left : rows_per_tile;
+    const int nsteps = (nrows_emit + (Q - 1) + 31) / 32;
+    const long long base = -(long long)fa.T - PAD + row_t0 * DROW;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + NSTG * STAGE_BYTES);
+    if (lane == 0) {
+        for (int s = 0; s < NSTG; s++) mbar_init(&mbar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    auto issue = [&](int i) {
+        if (i >= nsteps) return;
+        const int slot = i % NSTG;
+        unsigned char* dst = smem_raw + slot * STAGE_BYTES;
+        const long long s0 = base + (long long)i * (32 * DROW);
+        if (s0 >= 0 && s0 + 32 * DROW <= fa.count) {
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&mbar[slot], STAGE_BYTES);
+                tma_bulk_g2s(dst, fa.in + s0, STAGE_BYTES, &mbar[slot]);
+            }
+        } else {
+            VStream<float2> xs{fa.hist, fa.in, fa.H};
+            for (int e = lane; e < 32 * DROW; e += 32) {
+                const int rr = e / DROW, cc = e - rr * DROW;
+                const long long idx = s0 + e;
+                reinterpret_cast<float2*>(dst + rr * PITCH)[cc] = idx < fa.count ? xs.at(idx) : make_float2(0.f, 0.f);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&mbar[slot]);
+        }
+    };
+    for (int i = 0; i < NSTG; i++) issue(i);
+    float2 old[NPH];
+#pragma unroll
+    for (int j = 0; j < NPH; j++) old[j] = make_float2(0.f, 0.f);
+    const bool tail_lane = lane >= 32 - (Q - 1);
+#pragma unroll 1
+    for (int i = 0; i < nsteps; i++) {
+        const int slot = i % NSTG;
+        mbar_wait(&mbar[slot], (uint32_t)((i / NSTG) & 1));
+        const ulonglong2* xrow = reinterpret_cast<const ulonglong2*>(smem_raw + slot * STAGE_BYTES + lane * PITCH);
+        f32x2_t X[DROW];                                 // (re, im) of the row's samples, as loaded
+#pragma unroll
+        for (int c = 0; c < DROW / 2; c++) {
+            const ulonglong2 v = xrow[c];
+            X[2 * c] = v.x;
+            X[2 * c + 1] = v.y;
+        }
+        __syncwarp();
+        issue(i + NSTG);
+        float2 yv[NPH];
+#pragma unroll
+        for (int j0 = 0; j0 < NPH; j0 += 2) {
+            constexpr int NJ = 2;
+            f32x2_t acc[NJ][Q];
+#pragma unroll
+            for (int c4 = 0; c4 < DROW / 4; c4++) {      // four columns per 128-bit constant-bank tap load
+#pragma unroll
+                for (int jj = 0; jj < NJ; jj++) {
+                    if (j0 + jj >= NPH) continue;
+#pragma unroll
+                    for (int q = 0; q < Q; q++) {
+                        const bool l0 = firrow_live(j0 + jj, q, 2 * c4, D, DROW, PAD, T);
+                        const bool l1 = firrow_live(j0 + jj, q, 2 * c4 + 1, D, DROW, PAD, T);
+                        if (l0 || l1) {
+                            const float4 g4 = *reinterpret_cast<const float4*>(&fa.g[j0 + jj][q * DROW + 4 * c4]);
+                            const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+                            for (int hh = 0; hh < 4; hh++) {
+                                const int col = 4 * c4 + hh;
+                                if ((hh < 2) ? l0 : l1) {
+                                    const f32x2_t g = pk2(gg[hh], gg[hh]);
+                                    if (col == 2 * firrow_first(j0 + jj, q, D, DROW, PAD, T)) acc[jj][q] = fmul2x(X[col], g);
+                                    else acc[jj][q] = ffma2x(X[col], g, acc[jj][q]);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int jj = 0; jj < NJ; jj++) {
+                const int j = j0 + jj;
+                if (j >= NPH) continue;
+                float2 cur = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < Q; q++) {
+                    if (firrow_first(j, q, D, DROW, PAD, T) >= 0) {
+                        const float2 sv = unpk2(acc[jj][q]);
+                        if (q == 0) {
+                            cur = sv;
+                        } else {
+                            float2 p;
+                            p.x = __shfl_sync(0xffffffffu, sv.x, (lane + q) & 31);
+                            p.y = __shfl_sync(0xffffffffu, sv.y, (lane + q) & 31);
+                            if (lane + q < 32) cur = __fadd2_rn(cur, p);
+                            else old[j] = __fadd2_rn(old[j], p);
+                        }
+                    }
+                }
+                yv[j] = tail_lane ? old[j] : cur;
+                if (tail_lane) old[j] = cur;
+            }
+        }
+        const int rrel = 32 * i + lane - (tail_lane ? 32 : 0);
+        if (rrel >= 0 && rrel < nrows_emit) {
+            const long long k = (row_t0 + rrel) * NPH;
+            float2* o = fa.out + k;
+#pragma unroll
+            for (int j = 0; j < NPH; j++)
+                if (k + j < fa.n_out) o[j] = yv[j];
+        }
+    }
+}
+
 // ---- host side -------------------------------------------------------------------------------------
 bool firrow_supported(int T, int D) {
     static const bool on = getenv("QDSP_FIRROW") ? atoi(getenv("QDSP_FIRROW")) != 0 : true;
@@ -229,7 +366,14 @@ int launch_firrow(const float* taps_host, int T, int D, const float2* hist, floa
     const int rows_per_tile = 32 * fa.nstep - (Q - 1);
     const long long tiles = (nrows + rows_per_tile - 1) / rows_per_tile;
     static const int nstg_env = getenv("QDSP_FIRROW_NSTG") ? atoi(getenv("QDSP_FIRROW_NSTG")) : 2;   // 2 slots: 15 warps per SM (315 GS/s); 3 slots: 10 (310)
-    if (nstg_env == 2) {
+    static const int cplx_env = getenv("QDSP_FIRROW_CPLX") ? atoi(getenv("QDSP_FIRROW_CPLX")) : 1;
+    if (cplx_env) {
+        constexpr int NSTG = 2;
+        constexpr size_t smem = NSTG * 32 * (DROW * 8) + NSTG * 8 + 16;
+        auto kern = fir_rowcplx_kernel<4, DROW, Q, 127, PAD, NSTG>;
+        QDSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)tiles, 32, smem, s>>>(fa);
+    } else if (nstg_env == 2) {
         constexpr int NSTG = 2;
         constexpr size_t smem = NSTG * 32 * (DROW * 8) + NSTG * 8 + 16;
         auto kern = fir_rowphase_kernel<4, DROW, Q, 127, PAD, NSTG>;
