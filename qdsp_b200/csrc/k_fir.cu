@@ -14,6 +14,7 @@
 //   * the whole input window of a tile stays resident (NOUT + T - 1 samples), so the tap loop runs
 //     without any block-level barrier; two CTAs per SM overlap one tile's staging with the other's math.
 #include <stdlib.h>
+#include <mutex>
 #include <new>
 #include <vector>
 #include "decim_common.cuh"
@@ -29,6 +30,7 @@ struct FirPlan {
     int T = 0;
     int U = 0;                  // tap pairs per parity table
     float2* taps_dev = nullptr; // [2][U]: even table (h[2u], h[2u+1]); odd table (h[2u-1], h[2u])
+    float taps_host[256] = {};  // T <= 255: the taps again, for the constant-bank kernel (fir_cplx_kernel)
 };
 
 FirPlan* fir_plan_create(const float* taps, int T) {
@@ -36,6 +38,8 @@ FirPlan* fir_plan_create(const float* taps, int T) {
     FirPlan* p = new (std::nothrow) FirPlan();
     if (!p) return nullptr;
     p->T = T;
+    if (T <= 255)
+        for (int j = 0; j < T; j++) p->taps_host[j] = taps[j];
     int U = (T + 2) / 2;                        // enough pairs for the odd table's extra leading zero
     const int Upad = ((U + kFirR - 1) / kFirR) * kFirR;
     if ((Upad - U) * 33 <= U) U = Upad;         // long filters: round up to whole groups of R (< 3 % more work, leaner kernel);
@@ -434,12 +438,101 @@ int launch_fir_decim(FirDecimPlan* plan, const float2* hist, int H, const float2
     return 0;
 }
 
+// =================================================================================================
+// Short dense FIR (config 1a: 127 taps) with the taps in the constant bank -- the dense sibling of k_firrow.cu's
+// complex-pair form. A CTA is ONE warp with its own tile: K steps of 32 lanes x R = 9 consecutive outputs; the tile's raw
+// interleaved window (K*288 + T - 1 samples) arrives by ONE TMA bulk copy and is used as it lies: the packed FFMA2 operand
+// is the sample (re, im), the tap enters both halves as a scalar uniform-register operand (`FFMA2 R, R, UR.F32, R`), the
+// tap loop is fully unrolled (T is a template parameter), a lane slides a 9-sample register window: per tap ONE 64-bit
+// shared load (lane stride 72 bytes: conflict-free) and nine FFMA2. Against fir_dense_kernel for this length: no quad
+// re-layout pass, no parity tables, no horizontal adds, no shared-memory output exchange, no CTA barrier.
+// =================================================================================================
+struct FirCplxArgs {
+    const float2* hist;
+    const float2* in;
+    int H;
+    long long count;
+    float2* out;
+    alignas(16) float g[256];
+};
+template <int T, int K>
+__global__ void __launch_bounds__(32) fir_cplx_kernel(const __grid_constant__ FirCplxArgs fa) {
+    constexpr int R = 9, STEP = 32 * R, NOUT = K * STEP, NS = NOUT + T - 1;
+    static_assert((NS * 8) % 16 == 0 && ((T - 1) % 2) == 0, "the window is a whole number of 16-byte units and starts on an even sample");
+    __shared__ __align__(128) float2 win[NS];
+    __shared__ uint64_t s_mbar;
+    const int lane = threadIdx.x;
+    const long long n_t = (long long)blockIdx.x * NOUT;               // first output of the tile
+    const long long B = n_t - (T - 1);                                // sample index of win[0]
+    if (B >= 0 && B + NS <= fa.count) {
+        if (lane == 0) {
+            mbar_init(&s_mbar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_arrive_expect_tx(&s_mbar, (uint32_t)NS * 8u);
+            tma_bulk_g2s(win, fa.in + B, (uint32_t)NS * 8u, &s_mbar);
+        }
+        __syncwarp();
+        mbar_wait(&s_mbar, 0);
+    } else {   // history before sample 0 / ragged end: guarded fill
+        VStream<float2> xs{fa.hist, fa.in, fa.H};
+        for (int e = lane; e < NS; e += 32) {
+            const long long idx = B + e;
+            win[e] = idx < fa.count ? xs.at(idx) : make_float2(0.f, 0.f);
+        }
+        __syncwarp();
+    }
+#pragma unroll 1
+    for (int k = 0; k < K; k++) {
+        const f32x2_t* base = reinterpret_cast<const f32x2_t*>(win) + k * STEP + R * lane;
+        f32x2_t W[R], acc[R];
+#pragma unroll
+        for (int i = 0; i < R; i++) W[i] = base[i];
+#pragma unroll
+        for (int j = 0; j < T; j++) {
+            const f32x2_t g = pk2(fa.g[j], fa.g[j]);
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if (j == 0) acc[r] = fmul2x(W[(r + j) % R], g);
+                else acc[r] = ffma2x(W[(r + j) % R], g, acc[r]);
+            }
+            if (j + R <= T - 1 + R - 1) W[j % R] = base[j + R];       // element j is dead, element j + R enters
+        }
+        const long long n0 = n_t + k * STEP + R * lane;
+#pragma unroll
+        for (int r = 0; r < R; r++)
+            if (n0 + r < fa.count) fa.out[n0 + r] = unpk2(acc[r]);
+    }
+}
+
 int launch_fir_dense(FirPlan* plan, const float2* hist, int H, const float2* in, long long count, int lead,
                      float2* out, cudaStream_t s) {
     if (count <= 0) return 0;
     if (lead != 1) {
         set_last_error("fir_dense: only the FIR alignment (lead = 1) is implemented");
         return -1;
+    }
+    // constant-bank kernel: instantiated for 63 / 127 / 255 taps; a filter of T taps runs as the next instantiated length TT
+    // with TT - T leading zero taps (y[n] = sum_j g[j] x[n - (TT-1) + j], g[j] = h[j - (TT - T)]) when that costs < 1/3 more work
+    static const int cplx_env = getenv("QDSP_FIR_CPLX") ? atoi(getenv("QDSP_FIR_CPLX")) : 1;
+    const int TT = plan->T <= 63 ? 63 : (plan->T <= 127 ? 127 : 255);
+    if (cplx_env && plan->T <= 255 && 4 * plan->T > 3 * TT && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+        constexpr int K = 4;
+        static FirCplxArgs fa;
+        static std::mutex mtx;
+        std::lock_guard<std::mutex> lk(mtx);
+        fa.hist = hist;
+        fa.in = in;
+        fa.H = H;
+        fa.count = count;
+        fa.out = out;
+        const int z = TT - plan->T;
+        for (int j = 0; j < 256; j++) fa.g[j] = (j >= z && j < TT) ? plan->taps_host[j - z] : 0.0f;
+        const long long tiles = (count + K * 288 - 1) / (K * 288);
+        if (TT == 63) fir_cplx_kernel<63, K><<<(unsigned)tiles, 32, 0, s>>>(fa);
+        else if (TT == 127) fir_cplx_kernel<127, K><<<(unsigned)tiles, 32, 0, s>>>(fa);
+        else fir_cplx_kernel<255, K><<<(unsigned)tiles, 32, 0, s>>>(fa);
+        QDSP_LAUNCH_OK();
+        return 0;
     }
     VStream<float2> xs{hist, in, H};
     // short filters (config 1a: 127 taps): 128-thread CTAs with 1152-output tiles, 5 per SM; long ones keep the 2304-output

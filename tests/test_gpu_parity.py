@@ -893,3 +893,23 @@ print("ok")
     env = dict(os.environ, QDSP_COSTAS_WARP="1", PYTHONPATH=root)
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("ntaps", [50, 63, 100, 101, 126, 127, 200, 255])
+def test_fir_constant_bank_kernel_tap_counts(ntaps):
+    # fir_cplx_kernel (taps in the constant bank, instantiated for 63 / 127 / 255 taps): other lengths, even ones included,
+    # run with leading zero taps; ragged run() blocks incl. single samples and a block shorter than the filter, history
+    # carried in the handle
+    from qdsp_b200 import blocks as B, synth
+
+    P = loader.port()
+    rng = np.random.default_rng(ntaps)
+    taps = (rng.standard_normal(ntaps) * np.hanning(ntaps + 2)[1:-1] / np.sqrt(ntaps)).astype(np.float32)
+    n = 60_011
+    x = synth.uniform_cf32(7, 0, n)
+    yo = P.fir_cf32(taps, x)
+    f = B.FIR(B._TapsWindow(taps))
+    cuts = [0, 1, 40, 5000, 5001, 20_000, 20_000 + 4 * 288 * 7, n]
+    y = np.concatenate([f.process(x[a:b]) for a, b in zip(cuts[:-1], cuts[1:])])
+    assert y.shape == yo.shape
+    assert rel_l2(y, yo) <= 1e-5, rel_l2(y, yo)
