@@ -31,6 +31,7 @@ struct FirPlan {
     int U = 0;                  // tap pairs per parity table
     float2* taps_dev = nullptr; // [2][U]: even table (h[2u], h[2u+1]); odd table (h[2u-1], h[2u])
     float taps_host[256] = {};  // T <= 255: the taps again, for the constant-bank kernel (fir_cplx_kernel)
+    std::vector<float> taps_long;   // 255 < T <= 4095: the same for fir_longcplx_kernel
 };
 
 FirPlan* fir_plan_create(const float* taps, int T) {
@@ -40,6 +41,8 @@ FirPlan* fir_plan_create(const float* taps, int T) {
     p->T = T;
     if (T <= 255)
         for (int j = 0; j < T; j++) p->taps_host[j] = taps[j];
+    else if (T <= 4095)
+        p->taps_long.assign(taps, taps + T);
     int U = (T + 2) / 2;                        // enough pairs for the odd table's extra leading zero
     const int Upad = ((U + kFirR - 1) / kFirR) * kFirR;
     if ((Upad - U) * 33 <= U) U = Upad;         // long filters: round up to whole groups of R (< 3 % more work, leaner kernel);
@@ -504,6 +507,95 @@ __global__ void __launch_bounds__(32) fir_cplx_kernel(const __grid_constant__ Fi
     }
 }
 
+// =================================================================================================
+// Long dense FIR (config 3: 4095 taps) in the same form: the sample (re, im) is the packed operand, the tap a scalar
+// uniform-register operand from the constant bank (the whole filter travels as a kernel parameter, <= 4105 floats), a lane
+// slides a nine-sample register window (one conflict-free 64-bit shared load per tap). The tap loop cannot be unrolled
+// over 4095 taps: it runs in groups of 36 (the window rotation is static inside a group: 36 = 4 x 9) whose constant-bank
+// offset is a uniform register. A CTA of 8 warps shares ONE raw window (2304 + Tp - 1 samples, one TMA bulk copy, used as
+// it lies -- no quad re-layout, no parity tables); the filter is padded in FRONT with zeros to Tp = 36 m + 1 taps (the
+// window must start on an even sample, so Tp is odd: one leading tap, then m groups).
+// =================================================================================================
+constexpr int kFlG = 36;                    // taps per group
+constexpr int kFlMaxTp = 36 * 114 + 1;      // 4105: room for 4095 taps
+struct FirLongArgs {
+    const float2* hist;
+    const float2* in;
+    int H;
+    int Tp;                   // padded tap count, 36 m + 1
+    long long count;
+    float2* out;
+    alignas(16) float g[kFlMaxTp + 3];
+};
+__global__ void __launch_bounds__(256, 3) fir_longcplx_kernel(const __grid_constant__ FirLongArgs fa) {
+    constexpr int R = 9, NWARP = 8, NT = NWARP * 32, NOUT = NT * R;       // 2304 outputs per tile
+    extern __shared__ __align__(128) unsigned char fl_smem[];
+    float2* win = reinterpret_cast<float2*>(fl_smem);
+    __shared__ uint64_t s_mbar;
+    const int t = threadIdx.x;
+    const int Tp = fa.Tp;
+    const int NS = NOUT + Tp - 1;                                         // even: NOUT even, Tp odd
+    const long long n_t = (long long)blockIdx.x * NOUT;                   // first output of the tile
+    const long long B = n_t - (Tp - 1);                                   // sample index of win[0] (even)
+    if (B >= 0 && B + NS <= fa.count) {
+        if (t == 0) {
+            mbar_init(&s_mbar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (t == 0) {
+            mbar_arrive_expect_tx(&s_mbar, (uint32_t)NS * 8u);
+            tma_bulk_g2s(win, fa.in + B, (uint32_t)NS * 8u, &s_mbar);
+        }
+        mbar_wait(&s_mbar, 0);
+    } else {   // history before sample 0 / ragged end: guarded fill, 8 loads per thread in flight
+        VStream<float2> xs{fa.hist, fa.in, fa.H};
+        for (int e0 = t; e0 < NS; e0 += 8 * NT) {
+            float2 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int e = e0 + j * NT;
+                const long long idx = B + e;
+                v[j] = (e < NS && idx < fa.count) ? xs.at(idx) : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int e = e0 + j * NT;
+                if (e < NS) win[e] = v[j];
+            }
+        }
+        __syncthreads();
+    }
+    const f32x2_t* base = reinterpret_cast<const f32x2_t*>(win) + R * t;  // element e of this thread = win[9 t + e]
+    f32x2_t W[R], acc[R];
+#pragma unroll
+    for (int i = 0; i < R; i++) W[i] = base[i];
+    {   // the leading tap (j = 0): elements 0 .. 8, then element 9 replaces element 0
+        const f32x2_t g = pk2(fa.g[0], fa.g[0]);
+#pragma unroll
+        for (int r = 0; r < R; r++) acc[r] = fmul2x(W[r], g);
+        W[0] = base[R];
+    }
+    const int ngroups = (Tp - 1) / kFlG;
+#pragma unroll 1
+    for (int gi = 0; gi < ngroups; gi++) {
+        const int j0 = 1 + gi * kFlG;                                     // first tap of the group; j0 % 9 == 1
+        const float* gt = fa.g + j0;
+        const f32x2_t* bj = base + j0;
+#pragma unroll
+        for (int jj = 0; jj < kFlG; jj++) {
+            const f32x2_t g = pk2(gt[jj], gt[jj]);
+#pragma unroll
+            for (int r = 0; r < R; r++) acc[r] = ffma2x(W[(r + 1 + jj) % R], g, acc[r]);
+            W[(1 + jj) % R] = bj[jj + R];                                 // element j is dead, element j + 9 enters
+        }
+    }
+    const long long n0 = n_t + (long long)R * t;
+#pragma unroll
+    for (int r = 0; r < R; r++)
+        if (n0 + r < fa.count) fa.out[n0 + r] = unpk2(acc[r]);
+}
+
 int launch_fir_dense(FirPlan* plan, const float2* hist, int H, const float2* in, long long count, int lead,
                      float2* out, cudaStream_t s) {
     if (count <= 0) return 0;
@@ -531,6 +623,29 @@ int launch_fir_dense(FirPlan* plan, const float2* hist, int H, const float2* in,
         if (TT == 63) fir_cplx_kernel<63, K><<<(unsigned)tiles, 32, 0, s>>>(fa);
         else if (TT == 127) fir_cplx_kernel<127, K><<<(unsigned)tiles, 32, 0, s>>>(fa);
         else fir_cplx_kernel<255, K><<<(unsigned)tiles, 32, 0, s>>>(fa);
+        QDSP_LAUNCH_OK();
+        return 0;
+    }
+    static const int longcplx_env = getenv("QDSP_FIR_LONGCPLX") ? atoi(getenv("QDSP_FIR_LONGCPLX")) : 1;
+    if (longcplx_env && cplx_env && plan->T > 255 && plan->T <= 4095 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
+        !plan->taps_long.empty()) {
+        static FirLongArgs la;
+        static std::mutex mtx;
+        std::lock_guard<std::mutex> lk(mtx);
+        const int m = (plan->T - 1 + kFlG - 1) / kFlG;            // groups after the leading tap
+        const int Tp = m * kFlG + 1, z = Tp - plan->T;
+        la.hist = hist;
+        la.in = in;
+        la.H = H;
+        la.Tp = Tp;
+        la.count = count;
+        la.out = out;
+        for (int j = 0; j < kFlMaxTp + 3; j++) la.g[j] = (j >= z && j < Tp) ? plan->taps_long[j - z] : 0.0f;
+        const size_t smem = ((size_t)2304 + Tp + 8) * 8;
+        // per device (the attribute belongs to the current context), so set on every call: it is a cheap driver lookup
+        QDSP_CUDA_OK(cudaFuncSetAttribute(fir_longcplx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)2304 + kFlMaxTp + 8) * 8)));
+        const long long tiles = (count + 2304 - 1) / 2304;
+        fir_longcplx_kernel<<<(unsigned)tiles, 256, smem, s>>>(la);
         QDSP_LAUNCH_OK();
         return 0;
     }
