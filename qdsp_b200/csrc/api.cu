@@ -228,7 +228,16 @@ struct qdsp_resamp {
     FirDecimPlan* fplan = nullptr;   // small decimation (2..8): dense polyphase kernel
     int variant = 0;
     std::vector<float> taps;         // host copy (kernels that take their taps as launch parameters)
+    // the last single-kernel call (launch_firrow): when the very next library launch is this handle's next call on the same
+    // stream and its buffers do not touch that call's, the two grids may overlap (programmatic dependent launch)
+    long long last_serial = -1;
+    cudaStream_t last_stream = nullptr;
+    const char *last_in = nullptr, *last_out = nullptr;
+    size_t last_in_bytes = 0, last_out_bytes = 0;
 };
+static bool byte_ranges_overlap(const char* a, size_t na, const char* b, size_t nb) {
+    return a < b + nb && b < a + na;
+}
 
 extern "C" {
 
@@ -308,9 +317,22 @@ long long qdsp_resamp_process(qdsp_resamp* h, const void* in_dev, void* out_dev,
     if (regular && h->variant != 2 && h->part.total_out > 0 && firrow_supported(h->T, h->decim) &&
         (reinterpret_cast<uintptr_t>(in_dev) & 15) == 0) {
         // config 1b's geometry: row-per-lane kernel (TMA-fed, taps as uniform-register operands)
+        const char* ib = (const char*)in_dev;
+        const char* ob = (const char*)out_dev;
+        const size_t ibytes = (size_t)count * 8, obytes = (size_t)h->part.total_out * 8;
+        const bool overlap_prev = h->last_serial == g_launches.load() && h->last_stream == s &&
+                                  !byte_ranges_overlap(ib, ibytes, h->last_out, h->last_out_bytes) &&
+                                  !byte_ranges_overlap(ob, obytes, h->last_in, h->last_in_bytes) &&
+                                  !byte_ranges_overlap(ob, obytes, h->last_out, h->last_out_bytes);
         rc = launch_firrow(h->taps.data(), h->T, h->decim, (const float2*)h->hist.ptr(), (float2*)h->hist.buf[h->hist.cur ^ 1],
-                           h->hist.H, (const float2*)in_dev, count, h->part.total_out, (float2*)out_dev, s);
+                           h->hist.H, (const float2*)in_dev, count, h->part.total_out, (float2*)out_dev, s, overlap_prev);
         if (rc != 0) return -1;
+        h->last_serial = g_launches.load();
+        h->last_stream = s;
+        h->last_in = ib;
+        h->last_in_bytes = ibytes;
+        h->last_out = ob;
+        h->last_out_bytes = obytes;
         h->hist.cur ^= 1;            // the kernel's first CTA advanced the history tail
         return h->part.total_out;
     } else if (regular) {

@@ -206,6 +206,12 @@ __global__ void __launch_bounds__(32) fir_rowcplx_kernel(const __grid_constant__
     const int rows_per_tile = 32 * fa.nstep - (Q - 1);
     const long long row_t0 = (long long)blockIdx.x * rows_per_tile;
     const long long nrows_total = (fa.n_out + NPH - 1) / NPH;
+    // programmatic dependent launch (launch_firrow, overlap_prev): the next call of the same handle may start while this
+    // grid drains. Its only true dependencies are the history hand-over -- tile 0 reads `hist`, written by the previous
+    // call's CTA 0, and writes `hist_next`, which the previous call's tile 0 read -- so CTA 0 alone waits for the previous
+    // grid to complete; every other CTA reads only `in` and writes only `out` (the launcher has checked that they do not
+    // overlap the previous call's buffers). Without the launch attribute both instructions are no-ops.
+    if (blockIdx.x == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (fa.hist_next != nullptr && blockIdx.x == 0) {
         for (int j = lane; j < fa.H; j += 32) {
             const long long v = fa.count - fa.H + j;
@@ -245,6 +251,7 @@ __global__ void __launch_bounds__(32) fir_rowcplx_kernel(const __grid_constant__
         }
     };
     for (int i = 0; i < NSTG; i++) issue(i);
+    asm volatile("griddepcontrol.launch_dependents;");
     float2 old[NPH];
 #pragma unroll
     for (int j = 0; j < NPH; j++) old[j] = make_float2(0.f, 0.f);
@@ -335,7 +342,7 @@ bool firrow_supported(int T, int D) {
 }
 
 int launch_firrow(const float* taps_host, int T, int D, const float2* hist, float2* hist_next, int H, const float2* in,
-                  long long count, long long n_out, float2* out, cudaStream_t s) {
+                  long long count, long long n_out, float2* out, cudaStream_t s, bool overlap_prev) {
     if (n_out <= 0) return 0;
     constexpr int DROW = 28, Q = 6, NPH = 7;
     if (!firrow_supported(T, D) || (reinterpret_cast<uintptr_t>(in) & 15) != 0) {
@@ -372,7 +379,18 @@ int launch_firrow(const float* taps_host, int T, int D, const float2* hist, floa
         constexpr size_t smem = NSTG * 32 * (DROW * 8) + NSTG * 8 + 16;
         auto kern = fir_rowcplx_kernel<4, DROW, Q, 127, PAD, NSTG>;
         QDSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(unsigned)tiles, 32, smem, s>>>(fa);
+        static const int pdl_env = getenv("QDSP_PDL") ? atoi(getenv("QDSP_PDL")) : 1;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)tiles);
+        cfg.blockDim = dim3(32);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = (overlap_prev && pdl_env) ? 1 : 0;
+        QDSP_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, fa));
     } else if (nstg_env == 2) {
         constexpr int NSTG = 2;
         constexpr size_t smem = NSTG * 32 * (DROW * 8) + NSTG * 8 + 16;

@@ -94,7 +94,7 @@ int launch_fir_decim(FirDecimPlan* plan, const float2* hist, int H, const float2
 // ---- k_firrow.cu: row-per-lane decimating FIR for small decimations (config 1b: D = 4, 127 taps) ------------------
 bool firrow_supported(int T, int D);
 int launch_firrow(const float* taps_host, int T, int D, const float2* hist, float2* hist_next, int H, const float2* in,
-                  long long count, long long n_out, float2* out, cudaStream_t s);
+                  long long count, long long n_out, float2* out, cudaStream_t s, bool overlap_prev = false);
 
 // ---- k_recurrent.cu -----------------------------------------------------------------------------
 int launch_deemp(const float2* in, float2* out, long long count, float alpha, float* state, void* scratch,

@@ -913,3 +913,40 @@ def test_fir_constant_bank_kernel_tap_counts(ntaps):
     y = np.concatenate([f.process(x[a:b]) for a, b in zip(cuts[:-1], cuts[1:])])
     assert y.shape == yo.shape
     assert rel_l2(y, yo) <= 1e-5, rel_l2(y, yo)
+
+
+def test_resampler_back_to_back_calls_overlapped_launches():
+    # consecutive calls of ONE handle with disjoint buffers are launched so that their grids may overlap (programmatic
+    # dependent launch; only the history hand-over is ordered). 12 back-to-back calls on preloaded device buffers, nothing
+    # in between, against the oracle over the whole stream; then the same stream again with ONE output buffer reused by
+    # every call (overlap refused by the launcher: write-after-write) and with out == the previous call's in
+    from qdsp_b200 import blocks as B, synth
+
+    P = loader.port()
+    win = B.BlackmanWindow(300e3, 4 * 2.4e6 / 127, 2.4e6)
+    taps = P.blackman_taps(300e3, 4 * 2.4e6 / 127, 2.4e6)
+    ncall, n, blk = 12, 1 << 19, 1 << 17
+    x = synth.uniform_cf32(11, 0, ncall * n)
+    yo, _ = P.resamp_cf32(taps, 1, 4, x, blk)
+    ins = [B.DevBuf.from_numpy(x[i * n:(i + 1) * n]) for i in range(ncall)]
+    outs = [B.DevBuf(n // 4 * 8) for _ in range(ncall)]
+    r = B.PolyphaseResampler(win, 2.4e6, 0.6e6)
+    for i in range(ncall):
+        assert r.process_device(ins[i].ptr, outs[i].ptr, n, blk) == n // 4
+    y = np.concatenate([o.to_numpy(np.complex64, n // 4) for o in outs])
+    assert rel_l2(y, yo) <= 1e-5, rel_l2(y, yo)
+    # one output buffer for every call: each call's result is read back before the next call
+    r2 = B.PolyphaseResampler(win, 2.4e6, 0.6e6)
+    parts = []
+    for i in range(ncall):
+        r2.process_device(ins[i].ptr, outs[0].ptr, n, blk)
+        parts.append(outs[0].to_numpy(np.complex64, n // 4))
+    assert rel_l2(np.concatenate(parts), yo) <= 1e-5
+    # no read-back between the calls, the same output buffer: the last call's result must be the one that stays
+    r3 = B.PolyphaseResampler(win, 2.4e6, 0.6e6)
+    for i in range(ncall):
+        r3.process_device(ins[i].ptr, outs[1].ptr, n, blk)
+    last = outs[1].to_numpy(np.complex64, n // 4)
+    assert rel_l2(last, yo[(ncall - 1) * (n // 4):]) <= 1e-5
+    for b in ins + outs:
+        b.free()
