@@ -266,6 +266,7 @@ void qdsp_resamp_destroy(qdsp_resamp* h) {
     delete h;
 }
 int qdsp_resamp_set_taps(qdsp_resamp* h, const float* taps, int tapCount) {
+    h->last_serial = -1;      // state changed from the host: the next call does not overlap its predecessor
     int tpp = 0;
     std::vector<float> ph = build_phases(taps, tapCount, h->interp, &tpp);
     if (upload_floats(&h->phases_dev, ph) != 0) return -1;
@@ -366,12 +367,16 @@ int qdsp_resamp_get_history(qdsp_resamp* h, void* hist_host) {
     return 0;
 }
 int qdsp_resamp_set_history(qdsp_resamp* h, const void* hist_host) {
+    h->last_serial = -1;
     QDSP_CUDA_OK(cudaDeviceSynchronize());
     QDSP_CUDA_OK(cudaMemcpy(h->hist.buf[h->hist.cur], hist_host, (size_t)h->hist.H * h->hist.elem,
                             cudaMemcpyHostToDevice));
     return 0;
 }
-int qdsp_resamp_reset(qdsp_resamp* h) { return h->hist.reset(nullptr); }
+int qdsp_resamp_reset(qdsp_resamp* h) {
+    h->last_serial = -1;
+    return h->hist.reset(nullptr);
+}
 int qdsp_resamp_set_variant(qdsp_resamp* h, int variant) {
     h->variant = variant;
     return 0;
