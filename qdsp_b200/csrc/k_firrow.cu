@@ -361,7 +361,9 @@ int launch_firrow(const float* taps_host, int T, int D, const float2* hist, floa
     fa.T = T;
     fa.pad = PAD;
     static const int nstep_env = getenv("QDSP_FIRROW_NSTEP") ? atoi(getenv("QDSP_FIRROW_NSTEP")) : 0;
-    fa.nstep = nstep_env >= 2 ? nstep_env : 3;
+    // steps (of 32 rows) per one-warp tile: with consecutive calls overlapped the drain no longer favours the shortest tile
+    // (G samples/s at 2^24 per call, two boxes: 2: 346, 3: 348 / 359, 4: 347, 6: 355 / 368, 8: 357, 10: 332, 12: 273)
+    fa.nstep = nstep_env >= 2 ? nstep_env : 6;
     fa.out = out;
     fa.hist_next = hist_next;
     for (int j = 0; j < NPH; j++)
