@@ -1,7 +1,13 @@
-// qdsp_b200/csrc/k_fir.cu — register-blocked dense complex FIR for sm_100a (FIR<complex_t>::run, reference
+// qdsp_b200/csrc/k_fir.cu — dense complex FIR for sm_100a (FIR<complex_t>::run, reference
 // src/dsp/filter.h:51-74): y[n] = sum_j taps[j] * x[n - (T-1) + j], cf32 samples, real taps.
 //
-// FP32-bound (4*T flop per sample), so the kernel is built around the packed FFMA2 pipe:
+// Three kernels, all FP32-bound (4*T flop per sample) and built around the packed FFMA2 pipe:
+//   fir_cplx_kernel<T, K>   T = 63 / 127 / 255 (config 1a): taps in the constant bank, tap loop fully unrolled
+//   fir_longcplx_kernel     256 ... 4095 taps (config 3): taps in the constant bank, groups of 36 at a uniform offset
+//       both: packed operand = the sample (re, im) as it lies in the raw TMA window, tap = scalar uniform-register
+//       operand, nine-sample sliding register window (see the comments at the kernels, and DESIGN.md 6.2)
+//   fir_dense_kernel        any other case (longer filters, input not 16-byte aligned); also the engine of the
+//       small-decimation variant fir_decim_kernel. Its scheme:
 //   * samples are staged in shared memory as quads (re[2m], re[2m+1], im[2m], im[2m+1]); taps as pairs
 //     (h[2u], h[2u+1]). One FFMA2 then performs two real MACs of the SAME output,
 //         accRe += (re[2m], re[2m+1]) * (h[2u], h[2u+1])     (lanes summed once at the end)
