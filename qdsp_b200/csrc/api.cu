@@ -103,7 +103,13 @@ struct qdsp_fir {
     FirPlan* plan = nullptr;
     int variant = 0;
     std::vector<float> taps;
+    // the last single-kernel call (constant-bank kernels with the history advance folded in), see qdsp_resamp
+    long long last_serial = -1;
+    cudaStream_t last_stream = nullptr;
+    const char *last_in = nullptr, *last_out = nullptr;
+    size_t last_bytes = 0;
 };
+static bool fir_ranges_overlap(const char* a, size_t na, const char* b, size_t nb) { return a < b + nb && b < a + na; }
 
 extern "C" {
 
@@ -129,6 +135,7 @@ void qdsp_fir_destroy(qdsp_fir* h) {
     delete h;
 }
 int qdsp_fir_set_taps(qdsp_fir* h, const float* taps, int tapCount) {
+    h->last_serial = -1;
     h->taps.assign(taps, taps + tapCount);
     if (upload_floats(&h->taps_dev, h->taps) != 0) return -1;
     if (tapCount != h->T) {
@@ -146,9 +153,26 @@ long long qdsp_fir_process(qdsp_fir* h, const void* in_dev, void* out_dev, long 
     if (count == 0) return 0;
     const bool dense = h->plan && h->variant != 1;
     if (dense) {
+        const char *ib = (const char*)in_dev, *ob = (const char*)out_dev;
+        const size_t bytes = (size_t)count * 8;
+        const bool overlap_prev = h->last_serial == g_launches.load() && h->last_stream == s &&
+                                  !fir_ranges_overlap(ib, bytes, h->last_out, h->last_bytes) &&
+                                  !fir_ranges_overlap(ob, bytes, h->last_in, h->last_bytes) &&
+                                  !fir_ranges_overlap(ob, bytes, h->last_out, h->last_bytes);
+        bool advanced = false;
         if (launch_fir_dense(h->plan, (const float2*)h->hist.ptr(), h->hist.H, (const float2*)in_dev, count, 1,
-                             (float2*)out_dev, s) != 0)
+                             (float2*)out_dev, s, (float2*)h->hist.buf[h->hist.cur ^ 1], overlap_prev, &advanced) != 0)
             return -1;
+        if (advanced) {              // the kernel's first CTA advanced the history tail: one launch per call
+            h->hist.cur ^= 1;
+            h->last_serial = g_launches.load();
+            h->last_stream = s;
+            h->last_in = ib;
+            h->last_out = ob;
+            h->last_bytes = bytes;
+            return count;
+        }
+        h->last_serial = -1;
     } else {
         // FIR == polyphase bank with I = D = 1 read one sample later (filter.h:65 reads &buffer[i+1]);
         // y[i] = sum_j taps[j] * x[i - (T-1) + j]; the generic kernel's TPP-deep window with lead=1.
@@ -198,6 +222,7 @@ int qdsp_fir_get_history(qdsp_fir* h, void* hist_host) {
     return 0;
 }
 int qdsp_fir_set_history(qdsp_fir* h, const void* hist_host) {
+    h->last_serial = -1;
     QDSP_CUDA_OK(cudaDeviceSynchronize());
     if (h->hist.H > 0)
         QDSP_CUDA_OK(cudaMemcpy(h->hist.buf[h->hist.cur], hist_host, (size_t)h->hist.H * h->hist.elem,
@@ -205,9 +230,13 @@ int qdsp_fir_set_history(qdsp_fir* h, const void* hist_host) {
     return 0;
 }
 int qdsp_fir_import_tail(qdsp_fir* h, const void* tail_dev, int src_device, qdsp_stream_t s) {
+    h->last_serial = -1;
     return import_tail_impl(h->hist, tail_dev, src_device, as_stream(s));
 }
-int qdsp_fir_reset(qdsp_fir* h) { return h->hist.reset(nullptr); }
+int qdsp_fir_reset(qdsp_fir* h) {
+    h->last_serial = -1;
+    return h->hist.reset(nullptr);
+}
 int qdsp_fir_set_variant(qdsp_fir* h, int variant) {
     h->variant = variant;
     return 0;

@@ -462,8 +462,19 @@ struct FirCplxArgs {
     int H;
     long long count;
     float2* out;
+    float2* hist_next;        // when non-null: CTA 0 writes the advanced history tail here (filter.h:71)
     alignas(16) float g[256];
 };
+// Folded history advance + the ordering of overlapped consecutive calls (see k_firrow.cu / DESIGN.md 6.0c): the CTAs
+// that touch the carried history wait for the previous grid (a no-op without the launch attribute), everything else
+// reads only `in` and writes only `out`.
+__device__ __forceinline__ void fir_fold_history(const float2* hist, const float2* in, int H, long long count, float2* hist_next,
+                                                 int t, int nt) {
+    for (int j = t; j < H; j += nt) {
+        const long long v = count - H + j;
+        hist_next[j] = v >= 0 ? in[v] : hist[H + v];
+    }
+}
 template <int T, int K>
 __global__ void __launch_bounds__(32) fir_cplx_kernel(const __grid_constant__ FirCplxArgs fa) {
     constexpr int R = 9, STEP = 32 * R, NOUT = K * STEP, NS = NOUT + T - 1;
@@ -473,6 +484,8 @@ __global__ void __launch_bounds__(32) fir_cplx_kernel(const __grid_constant__ Fi
     const int lane = threadIdx.x;
     const long long n_t = (long long)blockIdx.x * NOUT;               // first output of the tile
     const long long B = n_t - (T - 1);                                // sample index of win[0]
+    if (blockIdx.x == 0 || B < 0) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (blockIdx.x == 0 && fa.hist_next != nullptr) fir_fold_history(fa.hist, fa.in, fa.H, fa.count, fa.hist_next, lane, 32);
     if (B >= 0 && B + NS <= fa.count) {
         if (lane == 0) {
             mbar_init(&s_mbar, 1);
@@ -480,9 +493,11 @@ __global__ void __launch_bounds__(32) fir_cplx_kernel(const __grid_constant__ Fi
             mbar_arrive_expect_tx(&s_mbar, (uint32_t)NS * 8u);
             tma_bulk_g2s(win, fa.in + B, (uint32_t)NS * 8u, &s_mbar);
         }
+        asm volatile("griddepcontrol.launch_dependents;");
         __syncwarp();
         mbar_wait(&s_mbar, 0);
     } else {   // history before sample 0 / ragged end: guarded fill
+        asm volatile("griddepcontrol.launch_dependents;");
         VStream<float2> xs{fa.hist, fa.in, fa.H};
         for (int e = lane; e < NS; e += 32) {
             const long long idx = B + e;
@@ -531,6 +546,7 @@ struct FirLongArgs {
     int Tp;                   // padded tap count, 36 m + 1
     long long count;
     float2* out;
+    float2* hist_next;        // when non-null: CTA 0 writes the advanced history tail here (filter.h:71)
     alignas(16) float g[kFlMaxTp + 3];
 };
 __global__ void __launch_bounds__(256, 3) fir_longcplx_kernel(const __grid_constant__ FirLongArgs fa) {
@@ -543,6 +559,9 @@ __global__ void __launch_bounds__(256, 3) fir_longcplx_kernel(const __grid_const
     const int NS = NOUT + Tp - 1;                                         // even: NOUT even, Tp odd
     const long long n_t = (long long)blockIdx.x * NOUT;                   // first output of the tile
     const long long B = n_t - (Tp - 1);                                   // sample index of win[0] (even)
+    if (blockIdx.x == 0 || B < 0) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (blockIdx.x == 0 && fa.hist_next != nullptr) fir_fold_history(fa.hist, fa.in, fa.H, fa.count, fa.hist_next, t, NT);
+    asm volatile("griddepcontrol.launch_dependents;");
     if (B >= 0 && B + NS <= fa.count) {
         if (t == 0) {
             mbar_init(&s_mbar, 1);
@@ -602,8 +621,27 @@ __global__ void __launch_bounds__(256, 3) fir_longcplx_kernel(const __grid_const
         if (n0 + r < fa.count) fa.out[n0 + r] = unpk2(acc[r]);
 }
 
+// hist_next / overlap_prev / advanced: when the constant-bank kernels take the call and `hist_next` is given, the kernel's
+// first CTA writes the advanced history tail there (*advanced = true: the caller flips its double buffer instead of
+// launching the advance kernel); overlap_prev lets the grid start while the previous call of the same handle drains
+static cudaError_t fir_launch_ex(const void* kern, dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool overlap, void* arg) {
+    static const int pdl_env = getenv("QDSP_PDL") ? atoi(getenv("QDSP_PDL")) : 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (overlap && pdl_env) ? 1 : 0;
+    void* args[1] = {arg};
+    return cudaLaunchKernelExC(&cfg, kern, args);
+}
 int launch_fir_dense(FirPlan* plan, const float2* hist, int H, const float2* in, long long count, int lead,
-                     float2* out, cudaStream_t s) {
+                     float2* out, cudaStream_t s, float2* hist_next, bool overlap_prev, bool* advanced) {
+    if (advanced) *advanced = false;
     if (count <= 0) return 0;
     if (lead != 1) {
         set_last_error("fir_dense: only the FIR alignment (lead = 1) is implemented");
@@ -623,13 +661,15 @@ int launch_fir_dense(FirPlan* plan, const float2* hist, int H, const float2* in,
         fa.H = H;
         fa.count = count;
         fa.out = out;
+        fa.hist_next = hist_next;
         const int z = TT - plan->T;
         for (int j = 0; j < 256; j++) fa.g[j] = (j >= z && j < TT) ? plan->taps_host[j - z] : 0.0f;
         const long long tiles = (count + K * 288 - 1) / (K * 288);
-        if (TT == 63) fir_cplx_kernel<63, K><<<(unsigned)tiles, 32, 0, s>>>(fa);
-        else if (TT == 127) fir_cplx_kernel<127, K><<<(unsigned)tiles, 32, 0, s>>>(fa);
-        else fir_cplx_kernel<255, K><<<(unsigned)tiles, 32, 0, s>>>(fa);
+        const void* kern = TT == 63 ? (const void*)fir_cplx_kernel<63, K>
+                                    : (TT == 127 ? (const void*)fir_cplx_kernel<127, K> : (const void*)fir_cplx_kernel<255, K>);
+        QDSP_CUDA_OK(fir_launch_ex(kern, dim3((unsigned)tiles), dim3(32), 0, s, overlap_prev, &fa));
         QDSP_LAUNCH_OK();
+        if (advanced && hist_next) *advanced = true;
         return 0;
     }
     static const int longcplx_env = getenv("QDSP_FIR_LONGCPLX") ? atoi(getenv("QDSP_FIR_LONGCPLX")) : 1;
@@ -646,13 +686,15 @@ int launch_fir_dense(FirPlan* plan, const float2* hist, int H, const float2* in,
         la.Tp = Tp;
         la.count = count;
         la.out = out;
+        la.hist_next = hist_next;
         for (int j = 0; j < kFlMaxTp + 3; j++) la.g[j] = (j >= z && j < Tp) ? plan->taps_long[j - z] : 0.0f;
         const size_t smem = ((size_t)2304 + Tp + 8) * 8;
         // per device (the attribute belongs to the current context), so set on every call: it is a cheap driver lookup
         QDSP_CUDA_OK(cudaFuncSetAttribute(fir_longcplx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)2304 + kFlMaxTp + 8) * 8)));
         const long long tiles = (count + 2304 - 1) / 2304;
-        fir_longcplx_kernel<<<(unsigned)tiles, 256, smem, s>>>(la);
+        QDSP_CUDA_OK(fir_launch_ex((const void*)fir_longcplx_kernel, dim3((unsigned)tiles), dim3(256), smem, s, overlap_prev, &la));
         QDSP_LAUNCH_OK();
+        if (advanced && hist_next) *advanced = true;
         return 0;
     }
     VStream<float2> xs{hist, in, H};

@@ -82,7 +82,8 @@ struct FirPlan;
 FirPlan* fir_plan_create(const float* taps, int T);
 void fir_plan_destroy(FirPlan* p);
 int launch_fir_dense(FirPlan* plan, const float2* hist, int H, const float2* in, long long count, int lead,
-                     float2* out, cudaStream_t s);
+                     float2* out, cudaStream_t s, float2* hist_next = nullptr, bool overlap_prev = false,
+                     bool* advanced = nullptr);
 
 // small-decimation FIR (interp = 1, 2 <= D <= 8): polyphase sub-streams through the dense inner loop
 struct FirDecimPlan;

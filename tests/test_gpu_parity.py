@@ -950,3 +950,37 @@ def test_resampler_back_to_back_calls_overlapped_launches():
     assert rel_l2(last, yo[(ncall - 1) * (n // 4):]) <= 1e-5
     for b in ins + outs:
         b.free()
+
+
+@pytest.mark.parametrize("ntaps", [127, 601])
+def test_fir_back_to_back_calls_overlapped_launches(ntaps):
+    # the constant-bank FIR kernels advance the history themselves (one launch per call) and consecutive calls of one
+    # handle with disjoint buffers may overlap on the GPU; 10 back-to-back calls incl. one shorter than the filter, then the
+    # refused case (one output buffer for every call) -- against the oracle over the whole stream
+    from qdsp_b200 import blocks as B, synth
+
+    P = loader.port()
+    rng = np.random.default_rng(ntaps)
+    taps = (rng.standard_normal(ntaps) * np.hanning(ntaps + 2)[1:-1] / np.sqrt(ntaps)).astype(np.float32)
+    sizes = [1 << 18, 1 << 18, 100, 1 << 18, 4 * 288 + 7, 1 << 18, 1 << 18, 2304 * 3, 1 << 18, 1 << 17]
+    x = synth.uniform_cf32(13, 0, sum(sizes))
+    yo = P.fir_cf32(taps, x)
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    ins = [B.DevBuf.from_numpy(x[offs[i]:offs[i + 1]]) for i in range(len(sizes))]
+    outs = [B.DevBuf(max(s, 2) * 8) for s in sizes]
+    f = B.FIR(B._TapsWindow(taps))
+    for i, s in enumerate(sizes):
+        assert f.process_device(ins[i].ptr, outs[i].ptr, s) == s
+    y = np.concatenate([outs[i].to_numpy(np.complex64, s) for i, s in enumerate(sizes)])
+    assert rel_l2(y, yo) <= 1e-5, rel_l2(y, yo)
+    big = B.DevBuf(max(sizes) * 8)
+    f2 = B.FIR(B._TapsWindow(taps))
+    parts = []
+    for i, s in enumerate(sizes):
+        f2.process_device(ins[i].ptr, big.ptr, s)
+        parts.append(big.to_numpy(np.complex64, s))
+    assert rel_l2(np.concatenate(parts), yo) <= 1e-5
+    # history read-back after the folded advance equals the stream's tail
+    assert np.array_equal(f.get_history(), x[-(ntaps - 1):])
+    for b in ins + outs + [big]:
+        b.free()
