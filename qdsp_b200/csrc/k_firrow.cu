@@ -335,6 +335,97 @@ __global__ void __launch_bounds__(32) fir_rowcplx_kernel(const __grid_constant__
     }
 }
 
+// ---- sliding-window variant -------------------------------------------------------------------------------------
+// The decimating sibling of k_fir.cu's fir_cplx_kernel: a CTA is one warp with its own tile (K steps of 32 lanes x R = 9
+// consecutive OUTPUTS = 36 consecutive input samples per lane), the tile's raw window arrives by one TMA bulk copy, the
+// sample (re, im) is the packed FFMA2 operand and the tap enters as a scalar uniform-register operand from the constant
+// bank. Output k0 + r at tap u reads window element 4 r + u (elements count from sample 4 k0 - T - 1: one pad sample keeps
+// the window 16-byte aligned, tap u = h[u - 1], u = 1..T): the lane keeps the 33 live elements in a statically rotated
+// register file of 36 and loads ONE pair (128 bits; lane stride 288 bytes: 2-way bank conflict, i.e. the wavefronts of a
+// conflict-free 64-bit load per element) every second tap: nine FFMA2 per tap, nothing else on the FMA pipe -- no row
+// partials to gather across lanes, no shuffles, no packs.
+struct FirSlideArgs {
+    const float2* hist;
+    const float2* in;
+    int H;
+    long long count;          // input samples of this call
+    long long n_out;          // outputs of this call
+    float2* out;
+    float2* hist_next;        // when non-null: CTA 0 writes the advanced history tail here (resampling.h:129)
+    alignas(16) float g[128]; // g[u] = h[u - 1], g[0] = 0
+};
+template <int T, int K>
+__global__ void __launch_bounds__(32) fir_slide4_kernel(const __grid_constant__ FirSlideArgs fa) {
+    constexpr int D = 4, R = 9, LSTEP = D * R, STEP_OUT = 32 * R, NOUT = K * STEP_OUT;
+    constexpr int EMAX = D * (R - 1) + T;                    // last window element a lane touches (159)
+    constexpr int NS = D * NOUT - LSTEP + EMAX + 1;          // samples of the tile's window (last lane, last step)
+    constexpr int NW = 36;                                   // register file: >= D*(R-1) + 1 live elements + the pair in flight
+    static_assert((T & 1) == 1 && (NS & 1) == 0 && NW % 2 == 0 && NW >= D * (R - 1) + 3, "geometry");
+    __shared__ __align__(128) float2 win[NS];
+    __shared__ uint64_t s_mbar;
+    const int lane = threadIdx.x;
+    // overlapped consecutive calls: see fir_rowcplx_kernel
+    if (blockIdx.x == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (fa.hist_next != nullptr && blockIdx.x == 0) {     // folded history advance: new_hist[j] = virtual[count - H + j]
+        for (int j = lane; j < fa.H; j += 32) {
+            const long long v = fa.count - fa.H + j;
+            fa.hist_next[j] = v >= 0 ? fa.in[v] : fa.hist[fa.H + v];
+        }
+    }
+    const long long k_t = (long long)blockIdx.x * NOUT;               // first output of the tile
+    if (k_t >= fa.n_out) return;
+    const long long B = D * k_t - T - 1;                              // sample index of win[0]
+    if (B >= 0 && B + NS <= fa.count) {
+        if (lane == 0) {
+            mbar_init(&s_mbar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_arrive_expect_tx(&s_mbar, (uint32_t)NS * 8u);
+            tma_bulk_g2s(win, fa.in + B, (uint32_t)NS * 8u, &s_mbar);
+        }
+        asm volatile("griddepcontrol.launch_dependents;");
+        __syncwarp();
+        mbar_wait(&s_mbar, 0);
+    } else {   // history before sample 0 / ragged end: guarded fill
+        asm volatile("griddepcontrol.launch_dependents;");
+        VStream<float2> xs{fa.hist, fa.in, fa.H};
+        for (int e = lane; e < NS; e += 32) {
+            const long long idx = B + e;
+            win[e] = idx < fa.count ? xs.at(idx) : make_float2(0.f, 0.f);
+        }
+        __syncwarp();
+    }
+#pragma unroll 1
+    for (int k = 0; k < K; k++) {
+        const ulonglong2* base = reinterpret_cast<const ulonglong2*>(win + k * (D * STEP_OUT) + LSTEP * lane);   // element pairs
+        f32x2_t W[NW], acc[R];
+#pragma unroll
+        for (int m = 0; m < (D * (R - 1) + 2) / 2; m++) {          // elements 0 .. 33
+            const ulonglong2 v = base[m];
+            W[2 * m] = v.x;
+            W[2 * m + 1] = v.y;
+        }
+#pragma unroll
+        for (int u = 1; u <= T; u++) {
+            const f32x2_t g = pk2(fa.g[u], fa.g[u]);
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if (u == 1) acc[r] = fmul2x(W[(D * r + u) % NW], g);
+                else acc[r] = ffma2x(W[(D * r + u) % NW], g, acc[r]);
+            }
+            // elements <= u are dead; tap u + 1 needs element u + 1 + D (R - 1): pairs (u + 33, u + 34) enter on odd u
+            if ((u & 1) && u + D * (R - 1) + 1 <= EMAX) {
+                const ulonglong2 v = base[(u + D * (R - 1) + 1) / 2];
+                W[(u + D * (R - 1) + 1) % NW] = v.x;
+                W[(u + D * (R - 1) + 2) % NW] = v.y;
+            }
+        }
+        const long long k0 = k_t + k * STEP_OUT + R * lane;
+#pragma unroll
+        for (int r = 0; r < R; r++)
+            if (k0 + r < fa.n_out) fa.out[k0 + r] = unpk2(acc[r]);
+    }
+}
+
 // ---- host side -------------------------------------------------------------------------------------
 bool firrow_supported(int T, int D) {
     static const bool on = getenv("QDSP_FIRROW") ? atoi(getenv("QDSP_FIRROW")) != 0 : true;
@@ -375,8 +466,34 @@ int launch_firrow(const float* taps_host, int T, int D, const float2* hist, floa
     const int rows_per_tile = 32 * fa.nstep - (Q - 1);
     const long long tiles = (nrows + rows_per_tile - 1) / rows_per_tile;
     static const int nstg_env = getenv("QDSP_FIRROW_NSTG") ? atoi(getenv("QDSP_FIRROW_NSTG")) : 2;   // 2 slots: 15 warps per SM (315 GS/s); 3 slots: 10 (310)
+    static const int slide_env = getenv("QDSP_FIRROW_SLIDE") ? atoi(getenv("QDSP_FIRROW_SLIDE")) : 0;
     static const int cplx_env = getenv("QDSP_FIRROW_CPLX") ? atoi(getenv("QDSP_FIRROW_CPLX")) : 1;
-    if (cplx_env) {
+    if (slide_env) {
+        static FirSlideArgs sa;
+        sa.hist = hist;
+        sa.in = in;
+        sa.H = H;
+        sa.count = count;
+        sa.n_out = n_out;
+        sa.out = out;
+        sa.hist_next = hist_next;
+        sa.g[0] = 0.0f;
+        for (int u = 1; u < 128; u++) sa.g[u] = taps_host[u - 1];
+        static const int pdl_env = getenv("QDSP_PDL") ? atoi(getenv("QDSP_PDL")) : 1;
+        const int K = slide_env == 2 ? 2 : 1;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)((n_out + K * 288 - 1) / (K * 288)));
+        cfg.blockDim = dim3(32);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = (overlap_prev && pdl_env) ? 1 : 0;
+        if (K == 2) QDSP_CUDA_OK(cudaLaunchKernelEx(&cfg, fir_slide4_kernel<127, 2>, sa));
+        else QDSP_CUDA_OK(cudaLaunchKernelEx(&cfg, fir_slide4_kernel<127, 1>, sa));
+    } else if (cplx_env) {
         constexpr int NSTG = 2;
         constexpr size_t smem = NSTG * 32 * (DROW * 8) + NSTG * 8 + 16;
         auto kern = fir_rowcplx_kernel<4, DROW, Q, 127, PAD, NSTG>;

@@ -984,3 +984,46 @@ def test_fir_back_to_back_calls_overlapped_launches(ntaps):
     assert np.array_equal(f.get_history(), x[-(ntaps - 1):])
     for b in ins + outs + [big]:
         b.free()
+
+
+def test_resampler_sliding_window_kernel_opt_in():
+    # QDSP_FIRROW_SLIDE=1 (read once per process, hence the subprocess): the constant-bank sliding-window decimate-by-4
+    # kernel -- faster than the row-per-lane default for calls of >= 2^26 samples -- on a ragged stream (history carried,
+    # a call shorter than the filter, a ragged last block) and on back-to-back overlapped calls, against the oracle
+    import os
+    import subprocess
+    import sys
+
+    code = r"""
+import numpy as np
+from oracle import loader
+from qdsp_b200 import blocks as B, synth
+P = loader.port()
+win = B.BlackmanWindow(300e3, 4 * 2.4e6 / 127, 2.4e6)
+taps = P.blackman_taps(300e3, 4 * 2.4e6 / 127, 2.4e6)
+def rel(a, b):
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+n = 1_500_000
+x = synth.uniform_cf32(17, 0, n)
+cuts = [0, 400_000, 400_040, 900_000, n]
+blocks = [b - a for a, b in zip(cuts[:-1], cuts[1:])]
+yo, _ = P.resamp_cf32(taps, 1, 4, x, blocks)
+r = B.PolyphaseResampler(win, 2.4e6, 0.6e6)
+y = np.concatenate([r.process(x[a:b], b - a) for a, b in zip(cuts[:-1], cuts[1:])])
+assert y.shape == yo.shape and rel(y, yo) <= 1e-5, rel(y, yo)
+ncall, m = 8, 1 << 18
+x2 = synth.uniform_cf32(19, 0, ncall * m)
+yo2, _ = P.resamp_cf32(taps, 1, 4, x2, m)
+ins = [B.DevBuf.from_numpy(x2[i * m:(i + 1) * m]) for i in range(ncall)]
+outs = [B.DevBuf(m // 4 * 8) for _ in range(ncall)]
+r2 = B.PolyphaseResampler(win, 2.4e6, 0.6e6)
+for i in range(ncall):
+    assert r2.process_device(ins[i].ptr, outs[i].ptr, m, m) == m // 4
+y2 = np.concatenate([o.to_numpy(np.complex64, m // 4) for o in outs])
+assert rel(y2, yo2) <= 1e-5, rel(y2, yo2)
+print("ok")
+"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, QDSP_FIRROW_SLIDE="1", PYTHONPATH=root)
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr

@@ -1,6 +1,6 @@
 """tools/size_sweep_cfg1.py — dev probe: configs 1a / 1b (127-tap FIR, FIR + decimate-by-4) at several launch sizes.
 Shows how much of a launch is ramp and drain: BASELINE's 2^24 samples are one 52 us launch for 1b.
-    python tools/size_sweep_cfg1.py"""
+    python tools/size_sweep_cfg1.py [cfg1a|cfg1b]"""
 import ctypes as C
 import json
 import os
@@ -14,6 +14,7 @@ from qdsp_b200 import blocks as B, lib  # noqa: E402
 L = lib.load()
 sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 win = B.BlackmanWindow(300e3, 4 * 2.4e6 / 127, 2.4e6)
+only = sys.argv[1] if len(sys.argv) > 1 else None
 for logn in (22, 24, 26, 27):
     n = 1 << logn
     nbuf = max(2, (1 << 29) // (n * 8) + 1)          # > L2 in rotation
@@ -23,6 +24,8 @@ for logn in (22, 24, 26, 27):
     for i, b in enumerate(xs):
         lib.check(L.qdsp_synth_uniform_cf32(b.ptr, 1, i * n, n, sp))
     for name, blk, args in (("cfg1a", B.FIR(win), ()), ("cfg1b", B.PolyphaseResampler(win, 2.4e6, 0.6e6), (524288,))):
+        if only and name != only:
+            continue
         it = [0]
 
         def step():
