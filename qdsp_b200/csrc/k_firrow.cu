@@ -468,7 +468,10 @@ int launch_firrow(const float* taps_host, int T, int D, const float2* hist, floa
     static const int nstg_env = getenv("QDSP_FIRROW_NSTG") ? atoi(getenv("QDSP_FIRROW_NSTG")) : 2;   // 2 slots: 15 warps per SM (315 GS/s); 3 slots: 10 (310)
     static const int slide_env = getenv("QDSP_FIRROW_SLIDE") ? atoi(getenv("QDSP_FIRROW_SLIDE")) : 0;
     static const int cplx_env = getenv("QDSP_FIRROW_CPLX") ? atoi(getenv("QDSP_FIRROW_CPLX")) : 1;
-    if (slide_env) {
+    // the sliding-window kernel wins away from BASELINE's 2^24-sample call (size sweep in DESIGN.md 6.0c): calls of >= 2^25
+    // samples take it unless QDSP_FIRROW_SLIDE=0 says otherwise; QDSP_FIRROW_SLIDE=1 / 2 force it (K = 1 / 2 steps per tile)
+    static const bool slide_auto = getenv("QDSP_FIRROW_SLIDE") == nullptr;
+    if (slide_env || (slide_auto && count >= (1ll << 25))) {
         static FirSlideArgs sa;
         sa.hist = hist;
         sa.in = in;
